@@ -1,0 +1,123 @@
+"""Pin the numpy oracle (oracle/unitair_oracle.py) against golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py) and the reference docs' known answers.
+CPU only."""
+import numpy as np
+import pytest
+
+from oracle import unitair_oracle as orc
+from conftest import assert_close
+
+
+def test_apply_operator_golden(golden):
+    arr = golden.arrays("apply_operator")
+    cases = golden.manifest["apply_operator"]
+    assert len(cases) > 60
+    for c in cases:
+        k = c["key"]
+        out = orc.apply_operator(arr[k + "_op"], c["qubits"], arr[k + "_state"])
+        assert out.shape == arr[k + "_out"].shape and out.dtype == arr[k + "_out"].dtype
+        assert_close(out, arr[k + "_out"], c["dtype"], what=str(c))
+
+
+def test_apply_all_qubits_golden(golden):
+    arr = golden.arrays("apply_all")
+    for c in golden.manifest["apply_all_qubits"]:
+        k = c["key"]
+        out = orc.apply_all_qubits(arr[k + "_op"], arr[k + "_state"])
+        assert out.shape == arr[k + "_out"].shape
+        assert_close(out, arr[k + "_out"], c["dtype"], factor=3, what=str(c))
+
+
+def test_apply_phase_golden(golden):
+    arr = golden.arrays("phase")
+    for c in golden.manifest["apply_phase"]:
+        k = c["key"]
+        out = orc.apply_phase(arr[k + "_angles"], arr[k + "_state"])
+        ref = arr[k + "_out"]
+        assert out.shape == ref.shape and out.dtype == ref.dtype, c
+        # the factors carry the ANGLES' precision (f32 angles on a c128 state -> f32 accuracy)
+        key = "c64" if c["angle_dtype"] == "f32" else ref.dtype
+        assert_close(out, ref, key, what=str(c))
+
+
+def test_reductions_golden(golden):
+    arr = golden.arrays("reductions")
+    for c in golden.manifest["reductions"]:
+        k = c["key"]
+        st, st2 = arr[k + "_state"], arr[k + "_state2"]
+        assert_close(orc.abs_squared(st), arr[k + "_abs2"], c["dtype"])
+        assert_close(orc.norm_squared(st), arr[k + "_norm2"], c["dtype"])
+        assert_close(orc.diag_expectation_value(arr[k + "_diag"], st), arr[k + "_dexp"], c["dtype"], factor=5)
+        assert_close(orc.diag_expectation_value(arr[k + "_diagb"], st), arr[k + "_dexpb"], c["dtype"], factor=5)
+        assert_close(orc.inner_product(st, st2), arr[k + "_inner"], c["dtype"], factor=5)
+
+
+def test_grads_golden(golden):
+    arr = golden.arrays("grads")
+    for c in golden.manifest["grads_apply_operator"]:
+        k = c["key"]
+        gu, gs = orc.apply_operator_grads(arr[k + "_op"], c["qubits"], arr[k + "_state"], arr[k + "_gout"])
+        assert gu.shape == arr[k + "_gop"].shape, c
+        assert gs.shape == arr[k + "_gstate"].shape, c
+        assert_close(gu, arr[k + "_gop"], c["dtype"], factor=5, what="grad_op " + str(c))
+        assert_close(gs, arr[k + "_gstate"], c["dtype"], factor=5, what="grad_state " + str(c))
+
+
+def test_circuit_c2_c4_golden(golden):
+    arr = golden.arrays("circuits")
+    m = golden.manifest["circuits"]
+    psi = arr["c2_state"]
+    for g in m["c2"]["gates"]:
+        psi = orc.apply_operator(arr[f"c2_g{g['g']}"], g["qubits"], psi)
+    assert_close(psi, arr["c2_out"], "c64", factor=10)
+    psi = arr["c4_state"]
+    nb = len(m["c4"]["blocks"]) // m["c4"]["layers"]
+    for l in range(m["c4"]["layers"]):
+        for g in m["c4"]["blocks"][l * nb:(l + 1) * nb]:
+            psi = orc.apply_operator(arr[f"c4_g{g['g']}"], g["qubits"], psi)
+        psi = orc.apply_phase(arr[f"c4_ang{l}"], psi)
+    assert_close(psi, arr["c4_out"], "c128", factor=10)
+
+
+def test_docs_known_answers():
+    """Known-answer vectors in the reference docs."""
+    q = np.array([[1, 5 - 1j], [5 + 1j, -1]], dtype=np.complex64)   # first_example.rst:74-75
+    ket0 = np.array([1, 0], dtype=np.complex64)
+    ket1 = np.array([0, 1], dtype=np.complex64)
+    np.testing.assert_allclose(orc.apply_operator(q, (0,), ket0), [1, 5 + 1j])
+    batch = np.stack([ket0, ket1])                                   # :123-124, 187-189
+    np.testing.assert_allclose(orc.apply_operator(q, (0,), batch), [[1, 5 + 1j], [5 - 1j, -1]])
+    h = np.array([[1, 1], [1, -1]], dtype=np.complex64) * 2 ** -0.5   # README.rst:165-166
+    np.testing.assert_allclose(orc.apply_operator(h, (0,), ket0), [0.70710678, 0.70710678], rtol=1e-6)
+    cnot = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex64)
+    s = np.zeros(4, np.complex64); s[0] = 1                          # README.rst:223-224 (Bell state)
+    s = orc.apply_operator(h, (0,), s)
+    s = orc.apply_operator(cnot, (0, 1), s)
+    np.testing.assert_allclose(s, [0.70710678, 0, 0, 0.70710678], rtol=1e-6, atol=1e-7)
+    # X on qubit 0 of |000> -> index 4 (qubit 0 is the most significant bit; conversions.py:43-45)
+    x = np.array([[0, 1], [1, 0]], dtype=np.complex64)
+    s = np.zeros(8, np.complex64); s[0] = 1
+    assert np.argmax(np.abs(orc.apply_operator(x, (0,), s))) == 4
+    # qubit order matters: CNOT on (1,0) != CNOT on (0,1)  (operations.py:82-86)
+    s = np.zeros(4, np.complex64); s[1] = 1   # |01>
+    assert np.argmax(np.abs(orc.apply_operator(cnot, (1, 0), s))) == 3
+    assert np.argmax(np.abs(orc.apply_operator(cnot, (0, 1), s))) == 1
+
+
+def test_oracle_errors():
+    st = np.zeros(8, np.complex64)
+    op = np.eye(2, dtype=np.complex64)
+    with pytest.raises(ValueError):
+        orc.apply_operator(op, (3,), st)
+    with pytest.raises(ValueError):
+        orc.apply_operator(op, (-1,), st)
+    with pytest.raises(ValueError):
+        orc.apply_operator(op, (0, 1), st)
+    with pytest.raises(ValueError):
+        orc.apply_operator(np.eye(4, dtype=np.complex64), (1, 1), st)
+    with pytest.raises(orc.StateShapeError):
+        orc.apply_operator(op, (0,), np.zeros(6, np.complex64))
+    with pytest.raises(RuntimeError):
+        orc.apply_operator(np.zeros((3, 3), np.complex64), (0,), st)
+    with pytest.raises(ValueError):
+        orc.apply_all_qubits(np.eye(4, dtype=np.complex64), st)
