@@ -1,0 +1,147 @@
+/*
+ * unitair_b200.h -- C ABI of the B200-native state-vector engine that sits behind
+ * unitair's gate-application API.
+ *
+ * The reference (qcware/qcware-unitair v0.3.0) is pure Python over PyTorch and has no
+ * FFI of its own; the boundary it exposes for this path is the Python function surface
+ * of src/unitair/simulation/operations.py and src/unitair/states/innerprod.py.  Each
+ * entry point below replaces the ATen work behind one of those functions (cited per
+ * function).  The host shim (qcware-unitair_b200/unitair_b200, Python like the
+ * reference) keeps the reference's signatures, validation and error types and calls
+ * these through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless named host_*.  No torch types cross the ABI.
+ *  - A state is `batch` contiguous rows of 2^num_qubits complex numbers (interleaved
+ *    re,im).  Qubit q is bit (num_qubits-1-q) of the row index: qubit 0 is the MOST
+ *    significant bit (src/unitair/states/conversions.py:43-45).
+ *  - A gate is row-major (2^k x 2^k); gate index MSB <-> qubits[0]
+ *    (src/unitair/simulation/operations.py:82-86).
+ *  - dtype: UA_C64 = complex64 (2 x f32), UA_C128 = complex128 (2 x f64).
+ *  - Every function returns UA_OK (0) or an error code, never throws; ua_last_error()
+ *    gives the message.  Work is enqueued on `stream` (a cudaStream_t) and is
+ *    asynchronous; outputs/workspaces are allocated by the caller.
+ *  - State pointers must be 16-byte aligned.
+ */
+#ifndef UNITAIR_B200_H
+#define UNITAIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UA_OK 0
+#define UA_ERR_INVALID 1      /* bad argument (caller bug)            */
+#define UA_ERR_UNSUPPORTED 2  /* valid request this build cannot run  */
+#define UA_ERR_CUDA 3         /* CUDA runtime error at launch         */
+
+#define UA_C64 0
+#define UA_C128 1
+
+#define UA_MAX_GATE_QUBITS 5        /* register/shared-memory kernels            */
+#define UA_MAX_GENERIC_GATE_QUBITS 10 /* slow generic kernel (out-of-place only) */
+#define UA_MAX_FUSED_GATES 64       /* gates per fused shared-memory pass        */
+#define UA_MAX_TILE_BITS 14
+
+/* library info ----------------------------------------------------------------- */
+int ua_version(void);
+const char *ua_last_error(void);
+/* number of kernels this library has launched so far in this process */
+unsigned long long ua_launch_count(void);
+
+/* Dense k-qubit gate, out = U . in (or U^H . in when adjoint != 0).
+ * Replaces apply_operator_tensor / act_first_qubits_tensor / permute_qubits_tensor
+ * (src/unitair/simulation/operations.py:151-186, 258-329, 626-654): no permute copies,
+ * target strides are computed in-kernel.
+ *   out            batch x 2^n, may alias `in` (in-place) when in_batch_stride == 2^n
+ *   in             state(s); row b starts at in + b*in_batch_stride (0 = one state
+ *                  broadcast to every gate of the batch, operations.py:304-309)
+ *   gate           row-major 2^k x 2^k; matrix b at gate + b*gate_batch_stride
+ *                  (0 = one gate shared by the whole batch)
+ *   host_qubits    k distinct unitair qubit indices in [0, n), in gate order       */
+int ua_apply_gate(int dtype, void *out, const void *in, const void *gate,
+                  int num_qubits, int k, const int *host_qubits,
+                  long long batch, long long in_batch_stride, long long gate_batch_stride,
+                  int adjoint, void *stream);
+
+/* Gradient of a real loss w.r.t. the gate (PyTorch's conjugate-Wirtinger convention;
+ * autograd of operations.py:322):
+ *   grad_gate[a,b] = sum_r grad_out[a,r] * conj(psi_in[b,r])
+ * per batch entry when gate_batch_stride != 0, summed over the batch when it is 0.
+ * workspace: ua_gate_grad_workspace_bytes() bytes of scratch.                        */
+size_t ua_gate_grad_workspace_bytes(int dtype, int num_qubits, int k, long long batch,
+                                    long long gate_batch_stride);
+int ua_gate_grad(int dtype, void *grad_gate, const void *grad_out, const void *psi_in,
+                 int num_qubits, int k, const int *host_qubits,
+                 long long batch, long long psi_batch_stride, long long gate_batch_stride,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fused diagonal phase: out[b,e] = exp(-+ i angles[b*abs + e*aes]) * in[b*ibs + e].
+ * Replaces torch.exp(-1j*angles)*state (operations.py:41-42) in one pass.
+ * conj_phase != 0 gives exp(+i angle) (the backward of apply_phase).
+ * angles are f32 for UA_C64 and f64 for UA_C128.                                     */
+int ua_apply_phase(int dtype, void *out, const void *in, const void *angles,
+                   long long elems, long long batch, long long in_batch_stride,
+                   long long angle_batch_stride, long long angle_elem_stride,
+                   int conj_phase, void *stream);
+
+/* Backward of apply_phase in one pass:
+ *   grad_state[b,e]  = exp(+i angle) * grad_out[b,e]
+ *   grad_angle[b,e]  = Im( conj(grad_out[b,e]) * exp(-i angle) * psi_in[b,e] )  (real)
+ * grad_state / grad_angle may be NULL to skip.                                       */
+int ua_phase_backward(int dtype, void *grad_state, void *grad_angle, const void *grad_out,
+                      const void *psi_in, const void *angles,
+                      long long elems, long long batch, long long in_batch_stride,
+                      long long angle_batch_stride, long long angle_elem_stride,
+                      void *stream);
+
+/* Reductions (src/unitair/states/innerprod.py:4-65), one read of the state each.
+ * Results are written in the state's real/complex precision.
+ * workspace: ua_reduce_workspace_bytes(batch, elems) bytes of scratch.               */
+size_t ua_reduce_workspace_bytes(long long batch, long long elems);
+int ua_abs_squared(int dtype, void *out_real, const void *in, long long count, void *stream);
+int ua_norm_squared(int dtype, void *out_real, const void *in, long long elems, long long batch,
+                    void *workspace, size_t workspace_bytes, void *stream);
+int ua_diag_expectation(int dtype, void *out_real, const void *diag_real, const void *in,
+                        long long elems, long long batch, long long diag_batch_stride,
+                        long long in_batch_stride,
+                        void *workspace, size_t workspace_bytes, void *stream);
+int ua_inner_product(int dtype, void *out_complex, const void *a, const void *b,
+                     long long elems, long long batch, long long a_batch_stride,
+                     long long b_batch_stride,
+                     void *workspace, size_t workspace_bytes, void *stream);
+
+/* Fused shared-memory pass: a list of dense gates (k <= 3 each) whose target bits all
+ * lie inside one tile = the low `tile_low_bits` index bits plus `num_high` chosen higher
+ * bit positions.  Every tile is staged once in shared memory, all gates are applied
+ * there, and the tile is written back: one HBM read+write for the whole list.
+ * This is the engine behind apply_all_qubits (operations.py:332-413) and the circuit
+ * API (apply_to_qubits-style fusion, operations.py:416-503).
+ *   total_bits        log2 of the flat index space covered (num_qubits [+ batch bits]);
+ *                     rows = total_amps >> total_bits independent spaces
+ *   host_high_pos     ascending bit positions (>= tile_low_bits) that join the tile
+ *   host_gate_k[g]    qubits of gate g; host_gate_bits[g*3+j] its BIT POSITIONS
+ *                     (gate order, MSB first); gate_mats: packed matrices, matrix g at
+ *                     gate_mats + host_gate_offset[g] (+ row*gate_row_stride if != 0) */
+int ua_apply_fused_pass(int dtype, void *out, const void *in, long long total_amps,
+                        int total_bits, int tile_low_bits, int num_high,
+                        const int *host_high_pos, int num_gates, const int *host_gate_k,
+                        const int *host_gate_bits, const long long *host_gate_offset,
+                        const void *gate_mats, long long gate_row_stride, int adjoint,
+                        void *stream);
+/* limits of the fused pass for this dtype: largest tile (bits) and the total number of
+ * complex matrix elements (sum of 4^k over the gates) one pass can hold */
+int ua_fused_limits(int dtype, int *max_tile_bits_out, int *max_matrix_elems_out);
+
+/* Bit-permutation of the index (qubit swap / permute, operations.py:506-654), one pass:
+ * out[b, i] = in[b, j] where bit host_src_bit[p] of j = bit p of i.                   */
+int ua_permute_bits(int dtype, void *out, const void *in, int num_bits, long long batch,
+                    const int *host_src_bit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNITAIR_B200_H */

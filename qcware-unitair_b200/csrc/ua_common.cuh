@@ -1,0 +1,74 @@
+// Shared device/host helpers for the unitair_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/unitair_b200.h"
+
+namespace ua {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char *fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+int check_launch(const char *what);   // counts the launch, maps cudaGetLastError()
+
+// ------------------------------------------------------------------ complex helpers
+template <typename R> struct CplxOf;
+template <> struct CplxOf<float>  { using type = float2;  };
+template <> struct CplxOf<double> { using type = double2; };
+
+// 16-byte vector that the streaming kernels move per load: 2 complex64 or 1 complex128
+template <typename R> struct VecOf;
+template <> struct VecOf<float>  { using type = float4;  static constexpr int APV = 2; };
+template <> struct VecOf<double> { using type = double2; static constexpr int APV = 1; };
+
+__device__ __forceinline__ float2  mk(float x, float y)   { return make_float2(x, y); }
+__device__ __forceinline__ double2 mk(double x, double y) { return make_double2(x, y); }
+
+template <typename C> __device__ __forceinline__ C cconj(C a) { a.y = -a.y; return a; }
+
+// acc += a*b (complex), 4 FMAs
+template <typename C> __device__ __forceinline__ void cfma(C &acc, const C a, const C b) {
+    acc.x = fma(a.x, b.x, acc.x);
+    acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y);
+    acc.y = fma(a.y, b.x, acc.y);
+}
+template <typename C> __device__ __forceinline__ C cmul(const C a, const C b) {
+    C r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+
+// ------------------------------------------------------------------ index helpers
+// insert a zero bit at position p (bits >= p move up by one)
+__host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t x, int p) {
+    const uint64_t lo = x & ((1ull << p) - 1ull);
+    return ((x >> p) << (p + 1)) | lo;
+}
+
+// ------------------------------------------------------------------ streaming ld/st
+// Streaming (evict-first) 16-byte accesses.  Plain coherent path (no .nc) so the
+// kernels stay correct when out aliases in.
+template <bool STREAM> __device__ __forceinline__ float4 ld16(const float4 *p) {
+    if (STREAM) return __ldcs(p);
+    return *p;
+}
+template <bool STREAM> __device__ __forceinline__ double2 ld16(const double2 *p) {
+    if (STREAM) return __ldcs(p);
+    return *p;
+}
+template <bool STREAM> __device__ __forceinline__ void st16(float4 *p, float4 v) {
+    if (STREAM) __stcs(p, v); else *p = v;
+}
+template <bool STREAM> __device__ __forceinline__ void st16(double2 *p, double2 v) {
+    if (STREAM) __stcs(p, v); else *p = v;
+}
+
+static inline bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
+static inline int ilog2(long long x) { int r = 0; while ((1ll << (r + 1)) <= x) ++r; return r; }
+
+}  // namespace ua

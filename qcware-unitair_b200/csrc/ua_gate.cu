@@ -1,0 +1,321 @@
+// Dense k-qubit gate application: out = U . in on arbitrary target bits, one HBM pass.
+//
+// Replaces the reference's permute -> contiguous -> einsum(bmm) -> permute -> contiguous
+// pipeline (src/unitair/simulation/operations.py:151-186, 258-329, 626-654).
+//
+// gate_direct_kernel: every thread owns `U` items; an item is the 2^KH 16-byte vectors
+// (2 complex64 or 1 complex128 each) that differ only in the target bits, so one item
+// holds complete 2^K-amplitude groups in registers.  Loads are issued before the gate
+// matrix is fetched, the (bit-order permuted, optionally adjoint) matrix sits in shared
+// memory, and results are streamed out with evict-first stores.  A target on index bit
+// 0 of a complex64 state lives inside the float4 (LOW = true): the pair is mixed in
+// registers and no extra vector is loaded.
+//
+// Algorithmic traffic: 16 B (complex64) / 32 B (complex128) per amplitude (read + write).
+#include "ua_common.cuh"
+
+namespace ua {
+
+struct GateArgs {
+    const void *in;
+    void *out;
+    const void *gate;
+    long long items_per_seg;    // items in one segment
+    long long seg_in_stride;    // 16-byte vectors between segments of `in` (0 = broadcast)
+    long long seg_out_stride;   // 16-byte vectors between segments of `out`
+    long long gate_seg_stride;  // complex elements between per-segment gates (0 = shared)
+    unsigned blocks_per_seg;
+    int vpos[UA_MAX_GATE_QUBITS];  // ascending target positions in vector-index space
+    int gbit[UA_MAX_GATE_QUBITS];  // gate-index bit of the i-th register-order target bit
+    int adjoint;
+};
+
+template <typename R, int K, bool LOW, int U, bool STREAM>
+__global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
+    using C = typename CplxOf<R>::type;
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    static_assert(!LOW || APV == 2, "an in-vector target exists only for complex64");
+    constexpr int KH = LOW ? K - 1 : K;   // targets that select WHICH vector
+    constexpr int NV = 1 << KH;           // vectors per item
+    constexpr int D = 1 << K;             // gate dimension
+    __shared__ C sU[D * D];
+
+    const unsigned bps = a.blocks_per_seg;
+    const long long seg = blockIdx.x / bps;
+    const unsigned chunk = blockIdx.x - (unsigned)seg * bps;
+
+    const V *__restrict__ in = reinterpret_cast<const V *>(a.in) + seg * a.seg_in_stride;
+    V *out = reinterpret_cast<V *>(a.out) + seg * a.seg_out_stride;
+
+    uint64_t off[KH > 0 ? KH : 1];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) off[i] = 1ull << a.vpos[i];
+
+    // ---- 1. issue all state loads first (independent of the gate) -------------------
+    V x[U][NV];
+    uint64_t base[U];
+    bool valid[U];
+    const long long item0 = (long long)chunk * (256 * U) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const long long item = item0 + (long long)u * 256;
+        valid[u] = item < a.items_per_seg;
+        uint64_t b = (uint64_t)item;
+#pragma unroll
+        for (int i = 0; i < KH; ++i) b = insert_zero(b, a.vpos[i]);
+        base[u] = b;
+        if (valid[u]) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                uint64_t idx = b;
+#pragma unroll
+                for (int i = 0; i < KH; ++i)
+                    if ((v >> i) & 1) idx |= off[i];
+                x[u][v] = ld16<STREAM>(in + idx);
+            }
+        }
+    }
+
+    // ---- 2. gate -> shared memory in register order (and adjoint if asked) -----------
+    {
+        const C *__restrict__ G = reinterpret_cast<const C *>(a.gate) + seg * a.gate_seg_stride;
+        for (int e = threadIdx.x; e < D * D; e += 256) {
+            const int s = e >> K, t = e & (D - 1);
+            int gi = 0, gj = 0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                gi |= ((s >> i) & 1) << a.gbit[i];
+                gj |= ((t >> i) & 1) << a.gbit[i];
+            }
+            C val;
+            if (a.adjoint) val = cconj(G[gj * D + gi]);
+            else val = G[gi * D + gj];
+            sU[e] = val;
+        }
+    }
+    __syncthreads();
+
+    // small gates live in registers
+    constexpr bool UREG = (K <= 2);
+    C ur[UREG ? D * D : 1];
+    if (UREG) {
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) ur[e] = sU[e];
+    }
+    auto Uat = [&](int s, int t) -> C { return UREG ? ur[s * D + t] : sU[s * D + t]; };
+
+    // ---- 3. multiply and stream out -------------------------------------------------
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+#pragma unroll
+        for (int ov = 0; ov < NV; ++ov) {
+            V res;
+            if constexpr (APV == 1) {
+                C acc = mk(R(0), R(0));
+#pragma unroll
+                for (int t = 0; t < D; ++t) cfma(acc, Uat(ov, t), x[u][t]);
+                res = acc;
+            } else if constexpr (LOW) {
+                C acc0 = mk(R(0), R(0)), acc1 = mk(R(0), R(0));
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    const V xv = x[u][t >> 1];
+                    const C amp = (t & 1) ? mk(xv.z, xv.w) : mk(xv.x, xv.y);
+                    cfma(acc0, Uat(2 * ov, t), amp);
+                    cfma(acc1, Uat(2 * ov + 1, t), amp);
+                }
+                res = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
+            } else {
+                C acc0 = mk(R(0), R(0)), acc1 = mk(R(0), R(0));
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    const C g = Uat(ov, t);
+                    cfma(acc0, g, mk(x[u][t].x, x[u][t].y));
+                    cfma(acc1, g, mk(x[u][t].z, x[u][t].w));
+                }
+                res = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
+            }
+            uint64_t idx = base[u];
+#pragma unroll
+            for (int i = 0; i < KH; ++i)
+                if ((ov >> i) & 1) idx |= off[i];
+            st16<STREAM>(out + idx, res);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic out-of-place kernel for 5 < k <= 10: one thread per output amplitude.  Slow
+// (re-reads through L1/L2) but complete; the reference accepts any k.
+struct GenericArgs {
+    const void *in;
+    void *out;
+    const void *gate;
+    long long total;           // batch * 2^n output amplitudes
+    long long in_batch_stride; // amplitudes
+    long long gate_batch_stride;
+    int n, k;
+    int pos[UA_MAX_GENERIC_GATE_QUBITS];  // bit position of qubits[j]
+    int adjoint;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) gate_generic_kernel(const GenericArgs a) {
+    using C = typename CplxOf<R>::type;
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.total) return;
+    const long long b = i >> a.n;
+    const uint64_t e = (uint64_t)i & ((1ull << a.n) - 1ull);
+    const int D = 1 << a.k;
+    uint64_t mask = 0;
+    int row = 0;
+    for (int j = 0; j < a.k; ++j) {
+        mask |= 1ull << a.pos[j];
+        row |= (int)((e >> a.pos[j]) & 1ull) << (a.k - 1 - j);
+    }
+    const uint64_t ebase = e & ~mask;
+    const C *__restrict__ in = reinterpret_cast<const C *>(a.in) + b * a.in_batch_stride;
+    const C *__restrict__ G = reinterpret_cast<const C *>(a.gate) + b * a.gate_batch_stride;
+    C acc = mk(R(0), R(0));
+    for (int t = 0; t < D; ++t) {
+        uint64_t idx = ebase;
+        for (int j = 0; j < a.k; ++j)
+            idx |= (uint64_t)((t >> (a.k - 1 - j)) & 1) << a.pos[j];
+        const C g = a.adjoint ? cconj(G[t * D + row]) : G[row * D + t];
+        cfma(acc, g, in[idx]);
+    }
+    reinterpret_cast<C *>(a.out)[i] = acc;
+}
+
+// ---------------------------------------------------------------------------------------
+static int cache_policy() {
+    static int policy = -1;
+    if (policy < 0) {
+        const char *e = getenv("UA_CACHE_POLICY");  // 0 auto, 1 always stream, 2 never
+        policy = e ? atoi(e) : 0;
+    }
+    return policy;
+}
+
+template <typename R, int K, bool LOW, int U>
+static int launch_direct(const GateArgs &a, unsigned grid, bool stream_hint, cudaStream_t st) {
+    if (stream_hint) gate_direct_kernel<R, K, LOW, U, true><<<grid, 256, 0, st>>>(a);
+    else gate_direct_kernel<R, K, LOW, U, false><<<grid, 256, 0, st>>>(a);
+    return check_launch("gate_direct_kernel");
+}
+
+template <typename R, int K, int U>
+static int launch_direct_low(const GateArgs &a, unsigned grid, bool low, bool sh, cudaStream_t st) {
+    if constexpr (VecOf<R>::APV == 2) {
+        if (low) return launch_direct<R, K, true, U>(a, grid, sh, st);
+    }
+    return launch_direct<R, K, false, U>(a, grid, sh, st);
+}
+
+template <int K> struct UnrollFor { static constexpr int value = K == 1 ? 4 : (K <= 3 ? 2 : 1); };
+
+template <typename R>
+static int dispatch_direct(int k, const GateArgs &a, unsigned grid, bool low, bool sh, cudaStream_t st) {
+    switch (k) {
+        case 1: return launch_direct_low<R, 1, UnrollFor<1>::value>(a, grid, low, sh, st);
+        case 2: return launch_direct_low<R, 2, UnrollFor<2>::value>(a, grid, low, sh, st);
+        case 3: return launch_direct_low<R, 3, UnrollFor<3>::value>(a, grid, low, sh, st);
+        case 4: return launch_direct_low<R, 4, UnrollFor<4>::value>(a, grid, low, sh, st);
+        case 5: return launch_direct_low<R, 5, UnrollFor<5>::value>(a, grid, low, sh, st);
+    }
+    set_error("ua_apply_gate: k=%d out of range", k);
+    return UA_ERR_INVALID;
+}
+
+static int unroll_for(int k) { return k == 1 ? 4 : (k <= 3 ? 2 : 1); }
+
+}  // namespace ua
+
+using namespace ua;
+
+extern "C" int ua_apply_gate(int dtype, void *out, const void *in, const void *gate,
+                             int num_qubits, int k, const int *host_qubits, long long batch,
+                             long long in_batch_stride, long long gate_batch_stride,
+                             int adjoint, void *stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int n = num_qubits;
+    if (dtype != UA_C64 && dtype != UA_C128) { set_error("ua_apply_gate: bad dtype %d", dtype); return UA_ERR_INVALID; }
+    if (!out || !in || !gate || !host_qubits) { set_error("ua_apply_gate: null pointer"); return UA_ERR_INVALID; }
+    if (n < 1 || n > 48 || k < 1 || k > n) { set_error("ua_apply_gate: bad n=%d k=%d", n, k); return UA_ERR_INVALID; }
+    if (k > UA_MAX_GENERIC_GATE_QUBITS) { set_error("ua_apply_gate: k=%d > %d unsupported", k, UA_MAX_GENERIC_GATE_QUBITS); return UA_ERR_UNSUPPORTED; }
+    if (batch < 1) { set_error("ua_apply_gate: batch=%lld", batch); return UA_ERR_INVALID; }
+    const long long dim = 1ll << n;
+    const long long gdim2 = 1ll << (2 * k);
+    if (in_batch_stride != 0 && in_batch_stride != dim) { set_error("ua_apply_gate: in_batch_stride must be 0 or 2^n"); return UA_ERR_INVALID; }
+    if (gate_batch_stride != 0 && gate_batch_stride != gdim2) { set_error("ua_apply_gate: gate_batch_stride must be 0 or 4^k"); return UA_ERR_INVALID; }
+    if (((uintptr_t)out | (uintptr_t)in) & 15) { set_error("ua_apply_gate: state pointers must be 16-byte aligned"); return UA_ERR_INVALID; }
+    if (in_batch_stride == 0 && batch > 1 && out == in) { set_error("ua_apply_gate: broadcast input cannot alias output"); return UA_ERR_INVALID; }
+    uint64_t seen = 0;
+    int pos[UA_MAX_GENERIC_GATE_QUBITS];
+    for (int j = 0; j < k; ++j) {
+        const int q = host_qubits[j];
+        if (q < 0 || q >= n) { set_error("ua_apply_gate: qubit %d out of range [0,%d)", q, n); return UA_ERR_INVALID; }
+        if (seen & (1ull << q)) { set_error("ua_apply_gate: duplicate qubit %d", q); return UA_ERR_INVALID; }
+        seen |= 1ull << q;
+        pos[j] = n - 1 - q;
+    }
+
+    if (k > UA_MAX_GATE_QUBITS) {
+        if (out == in) { set_error("ua_apply_gate: k>%d is out-of-place only", UA_MAX_GATE_QUBITS); return UA_ERR_UNSUPPORTED; }
+        GenericArgs g;
+        g.in = in; g.out = out; g.gate = gate;
+        g.total = batch * dim;
+        g.in_batch_stride = in_batch_stride; g.gate_batch_stride = gate_batch_stride;
+        g.n = n; g.k = k; g.adjoint = adjoint;
+        for (int j = 0; j < k; ++j) g.pos[j] = pos[j];
+        const long long blocks = (g.total + 255) / 256;
+        if (blocks > 0x7fffffffll) { set_error("ua_apply_gate: grid too large"); return UA_ERR_UNSUPPORTED; }
+        if (dtype == UA_C64) gate_generic_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(g);
+        else gate_generic_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(g);
+        return check_launch("gate_generic_kernel");
+    }
+
+    // sort targets by bit position (ascending), remember their gate-index bit
+    int order[UA_MAX_GATE_QUBITS];
+    for (int j = 0; j < k; ++j) order[j] = j;
+    for (int i = 1; i < k; ++i)
+        for (int j = i; j > 0 && pos[order[j]] < pos[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+
+    GateArgs a;
+    a.in = in; a.out = out; a.gate = gate; a.adjoint = adjoint ? 1 : 0;
+    const int apv_log = (dtype == UA_C64) ? 1 : 0;       // log2(amplitudes per vector)
+    const bool low = (dtype == UA_C64) && pos[order[0]] == 0;
+    const int kh = low ? k - 1 : k;
+    for (int i = 0; i < UA_MAX_GATE_QUBITS; ++i) { a.vpos[i] = 0; a.gbit[i] = 0; }
+    for (int i = 0; i < k; ++i) a.gbit[i] = k - 1 - order[i];
+    for (int i = 0; i < kh; ++i) a.vpos[i] = pos[order[i + (low ? 1 : 0)]] - apv_log;
+
+    const long long vec_per_state = dim >> apv_log;
+    const long long items_per_state = vec_per_state >> kh;
+    const bool flat = (gate_batch_stride == 0) && (in_batch_stride == dim || batch == 1);
+    long long segs;
+    if (flat) {
+        segs = 1;
+        a.items_per_seg = items_per_state * batch;
+        a.seg_in_stride = 0; a.seg_out_stride = 0; a.gate_seg_stride = 0;
+    } else {
+        segs = batch;
+        a.items_per_seg = items_per_state;
+        a.seg_in_stride = in_batch_stride >> apv_log;
+        a.seg_out_stride = vec_per_state;
+        a.gate_seg_stride = gate_batch_stride;
+    }
+    const int U = unroll_for(k);
+    const long long bps = (a.items_per_seg + 256ll * U - 1) / (256ll * U);
+    const long long grid = bps * segs;
+    if (grid > 0x7fffffffll || bps > 0x7fffffffll) { set_error("ua_apply_gate: grid too large"); return UA_ERR_UNSUPPORTED; }
+    a.blocks_per_seg = (unsigned)bps;
+
+    const long long bytes = batch * dim * ((dtype == UA_C64) ? 8ll : 16ll);
+    const int pol = cache_policy();
+    const bool stream_hint = pol == 1 || (pol == 0 && bytes >= (96ll << 20));
+    if (dtype == UA_C64) return dispatch_direct<float>(k, a, (unsigned)grid, low, stream_hint, st);
+    return dispatch_direct<double>(k, a, (unsigned)grid, low, stream_hint, st);
+}

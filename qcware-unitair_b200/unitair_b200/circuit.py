@@ -1,0 +1,284 @@
+"""Circuit-level gate application: many gates per pass over the state.
+
+The reference applies one gate per call and pays 3-4 full-state passes for each
+(src/unitair/simulation/operations.py:151-186); its only fusion is multiplying 2x2s that
+hit the same qubit (apply_to_qubits, operations.py:416-503).  Here a list of gates is cut
+into *passes*: a pass is a run of gates whose target bits all fit inside one shared-memory
+tile (the low `low_bits` index bits plus up to `max_high` freely chosen higher bits), and
+each pass costs one read + one write of the state however many gates it holds
+(native entry ua_apply_fused_pass).  Gates that cannot join a pass (k > 3) go through the
+single-gate kernel.
+
+The planner is pure host integer work and is tested on CPU; the execution functions need
+CUDA tensors.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _engine
+from . import _lib as L
+
+MAX_FUSED_K = 3
+
+
+# --------------------------------------------------------------------------- #
+# planning (host only)
+# --------------------------------------------------------------------------- #
+@dataclass
+class TileGeometry:
+    total_bits: int      # index bits of one independent space (= num_qubits)
+    tile_bits: int       # T
+    low_bits: int        # L: always-resident contiguous low bits
+    max_high: int        # H = T - L
+
+
+@dataclass
+class Pass:
+    high: List[int] = field(default_factory=list)      # ascending bit positions >= low_bits
+    gates: List[int] = field(default_factory=list)     # indices into the gate list, in order
+    direct: bool = False                                # single big gate -> direct kernel
+
+
+def default_geometry(num_qubits: int, dtype: torch.dtype) -> TileGeometry:
+    """Tile shape used for a state of `num_qubits` qubits.
+
+    complex64: 2^13 amplitudes = 64 KiB per tile (3 tiles resident per SM), complex128:
+    2^12 = 64 KiB.  The low 7 (c64) / 6 (c128) bits are always in the tile, which makes
+    every global access a coalesced 1 KiB run.
+    """
+    if dtype == torch.complex128:
+        tile, low = 12, 6
+    else:
+        tile, low = 13, 7
+    tile = int(os.environ.get("UA_TILE_BITS", tile))
+    low = int(os.environ.get("UA_TILE_LOW_BITS", low))
+    tile = min(tile, num_qubits)
+    low = min(low, tile)
+    return TileGeometry(num_qubits, tile, low, tile - low)
+
+
+def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
+                max_gates: int = L.MAX_FUSED_GATES, max_mat_elems: int = 2048,
+                lookahead: int = 512) -> List[Pass]:
+    """Cut an ordered gate list into passes.
+
+    gate_bits[g] are the index-bit positions gate g acts on.  Gates are only reordered
+    across gates they share no bit with (a skipped gate blocks its bits for the rest of
+    the pass), so the product of the passes equals the original circuit.
+    """
+    n_gates = len(gate_bits)
+    done = [False] * n_gates
+    passes: List[Pass] = []
+    first = 0
+    while first < n_gates:
+        if done[first]:
+            first += 1
+            continue
+        k0 = len(gate_bits[first])
+        if k0 > MAX_FUSED_K:
+            passes.append(Pass(high=[], gates=[first], direct=True))
+            done[first] = True
+            continue
+        cur = Pass()
+        high = set()
+        blocked = set()
+        mat_elems = 0
+        scanned = 0
+        for g in range(first, n_gates):
+            if done[g]:
+                continue
+            scanned += 1
+            if scanned > lookahead or len(cur.gates) >= max_gates:
+                break
+            bits = gate_bits[g]
+            k = len(bits)
+            if k > MAX_FUSED_K or any(b in blocked for b in bits):
+                blocked.update(bits)
+                continue
+            need = {b for b in bits if b >= geo.low_bits} - high
+            if len(high) + len(need) > geo.max_high or mat_elems + 4 ** k > max_mat_elems:
+                blocked.update(bits)
+                continue
+            high |= need
+            mat_elems += 4 ** k
+            cur.gates.append(g)
+            done[g] = True
+            if len(blocked) >= geo.total_bits:
+                break
+        # fill the unused high slots with the lowest free positions so the tile is full
+        p = geo.low_bits
+        while len(high) < geo.max_high and p < geo.total_bits:
+            if p not in high:
+                high.add(p)
+            p += 1
+        cur.high = sorted(high)
+        passes.append(cur)
+    return passes
+
+
+# --------------------------------------------------------------------------- #
+# execution
+# --------------------------------------------------------------------------- #
+def _run_pass(out, inp, n, batch, geo: TileGeometry, p: Pass, gate_bits, offsets, mats,
+              row_stride, adjoint=False):
+    dev = inp.device
+    ks = [len(gate_bits[g]) for g in p.gates]
+    bits_flat = []
+    for g in p.gates:
+        b = list(gate_bits[g])
+        bits_flat += b + [0] * (3 - len(b))
+    offs = [offsets[g] for g in p.gates]
+    low = geo.tile_bits - len(p.high)
+    with L.on_device(dev):
+        L.check(L.lib().ua_apply_fused_pass(
+            L.dtype_code(inp.dtype), out.data_ptr(), inp.data_ptr(), batch << n, n, low,
+            len(p.high), L.int_array(p.high) if p.high else None, len(p.gates),
+            L.int_array(ks), L.int_array(bits_flat), L.ll_array(offs), mats.data_ptr(),
+            row_stride, 1 if adjoint else 0, L.stream_ptr(dev)))
+
+
+def _pack_gates(mats_list, batch_shape, dtype, device):
+    """One flat device buffer holding every gate matrix; returns (buffer, offsets, row_stride)."""
+    offsets = []
+    off = 0
+    for m in mats_list:
+        offsets.append(off)
+        off += m.shape[-1] * m.shape[-2]
+    any_batched = any(m.dim() > 2 for m in mats_list)
+    if not any_batched:
+        buf = torch.cat([m.reshape(-1) for m in mats_list])
+        return buf.contiguous(), offsets, 0
+    rows = []
+    for m in mats_list:
+        if m.dim() == 2:
+            rows.append(m.reshape(1, -1).expand(_engine._prod(batch_shape), -1))
+        else:
+            rows.append(m.expand(tuple(batch_shape) + m.shape[-2:]).reshape(_engine._prod(batch_shape), -1))
+    buf = torch.cat(rows, dim=1).contiguous()
+    return buf, offsets, off
+
+
+def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torch.Tensor,
+                in_place: bool = False) -> torch.Tensor:
+    """Apply an ordered list of (qubits, operator) to a state in vector layout.
+
+    Equivalent to calling simulation.apply_operator for each gate in turn.  Operators are
+    (2^k, 2^k) or share the state's batch dims.  When no gradient is needed the list is
+    executed as fused shared-memory passes; with autograd it falls back to one native
+    gate kernel (and one autograd node) per gate.
+    """
+    from . import states
+    from .simulation import operations as ops
+    n = states.count_qubits(state)
+    gates = [([int(q) for q in qs], m) for qs, m in gates]
+    needs_grad = torch.is_grad_enabled() and (
+        state.requires_grad or any(m.requires_grad for _, m in gates))
+    batch_shape = tuple(state.shape[:-1])
+    simple = all(m.dim() == 2 or tuple(m.shape[:-2]) == batch_shape for _, m in gates)
+    if needs_grad or not simple or not state.is_complex() or any(m.dtype != state.dtype for _, m in gates):
+        out = state
+        for qs, m in gates:
+            out = ops.apply_operator(m, qs, out)
+        return out
+    L.require_cuda(state, *[m for _, m in gates])
+    for qs, m in gates:
+        k = states.count_qubits_gate_matrix(m)
+        if len(qs) != k or len(set(qs)) != k or not set(qs).issubset(range(n)):
+            raise ValueError(f"qubits={qs} is not a valid target list for a {k}-qubit operator "
+                             f"on {n} qubits")
+    if not gates:
+        return state if in_place else state.clone()
+    batch = _engine._prod(batch_shape)
+    if batch == 0:
+        return state if in_place else state.clone()
+    cur = _engine._aligned(state)
+    if in_place and cur.data_ptr() != state.data_ptr():
+        raise RuntimeError("in_place=True needs a contiguous, 16-byte aligned state")
+    geo = default_geometry(n, state.dtype)
+    gate_bits = [[n - 1 - q for q in qs] for qs, _ in gates]
+    mats, offsets, row_stride = _pack_gates([m for _, m in gates], batch_shape, state.dtype,
+                                            state.device)
+    out = cur if in_place else None
+    for p in plan_passes(gate_bits, geo):
+        src = cur if out is None else out
+        if out is None:
+            out = torch.empty_like(cur)
+        if p.direct:
+            g = p.gates[0]
+            qs, m = gates[g]
+            m_c = _engine._aligned(m)
+            gate_stride = 0 if m.dim() == 2 else 4 ** len(qs)
+            _engine.launch_gate(out, src, m_c, n, len(qs), qs, batch, 1 << n, gate_stride, False)
+        else:
+            _run_pass(out, src, n, batch, geo, p, gate_bits, offsets, mats, row_stride)
+    return out
+
+
+def apply_same_gate_all_qubits(operator: torch.Tensor, state: torch.Tensor, n: int) -> torch.Tensor:
+    """The same 2x2 (shared or per batch entry) on every qubit, qubit 0 first
+    (src/unitair/simulation/operations.py:369-413)."""
+    op_batch = tuple(operator.shape[:-2])
+    st_batch = tuple(state.shape[:-1])
+    if op_batch and not st_batch:
+        state = state.expand(op_batch + state.shape[-1:])
+    elif op_batch and op_batch != st_batch:
+        out_batch = tuple(torch.broadcast_shapes(op_batch, st_batch))
+        if len(op_batch) > len(st_batch):
+            raise RuntimeError(f"operator batch dims {op_batch} cannot be broadcast to state "
+                               f"batch dims {st_batch}")
+        operator = operator.expand(out_batch + (2, 2))
+        state = state.expand(out_batch + state.shape[-1:])
+    return apply_gates([([q], operator) for q in range(n)], state)
+
+
+class _PermuteQubits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state, permutation, n):
+        ctx.inverse = [0] * n
+        for slot, item in enumerate(permutation):
+            ctx.inverse[item] = slot
+        ctx.n = n
+        return _permute_launch(state, permutation, n)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        return _permute_launch(_engine._aligned(grad), ctx.inverse, ctx.n), None, None
+
+
+def _permute_launch(state, permutation, n):
+    dev = state.device
+    out = torch.empty_like(state)
+    batch = _engine._prod(state.shape[:-1])
+    if batch == 0:
+        return out
+    # output qubit i takes input qubit permutation[i]; qubit q is index bit n-1-q
+    src = [0] * n
+    for i, p in enumerate(permutation):
+        src[n - 1 - i] = n - 1 - p
+    with L.on_device(dev):
+        L.check(L.lib().ua_permute_bits(L.dtype_code(state.dtype), out.data_ptr(), state.data_ptr(),
+                                        n, batch, L.int_array(src), L.stream_ptr(dev)))
+    return out
+
+
+def permute_qubits_native(permutation, state, n):
+    if not state.is_complex():
+        # pure data movement: view real data as complex pairs is not possible for odd
+        # layouts, so use the stock permute (same device)
+        from . import states
+        t = states.to_tensor_layout(state)
+        nb = t.dim() - n
+        return states.to_vector_layout(
+            t.permute(list(range(nb)) + [nb + p for p in permutation]), n)
+    st = _engine._aligned(state)
+    if n == 0:
+        return st.clone()
+    if torch.is_grad_enabled() and st.requires_grad:
+        return _PermuteQubits.apply(st, list(permutation), n)
+    return _permute_launch(st, list(permutation), n)

@@ -1,0 +1,135 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/unitair_b200.h
+declares, the host shim validates like the reference, the pass planner is correct, and the
+product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import unitair_b200 as ua
+from unitair_b200 import _lib, circuit
+from oracle import unitair_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "unitair_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = sorted(set(re.findall(r"\b(ua_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 15, names
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert _lib.lib().ua_version() >= 100
+
+
+def test_no_cpu_fallback():
+    st = torch.zeros(8, dtype=torch.complex64)
+    op = torch.eye(2, dtype=torch.complex64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.simulation.apply_operator(op, (0,), st)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.simulation.apply_all_qubits(op, st)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.simulation.apply_phase(torch.zeros(8), st)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.abs_squared(st)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.diag_expectation_value(torch.zeros(8), st)
+
+
+def test_validation_matches_reference_error_types():
+    st = torch.zeros(8, dtype=torch.complex64)
+    op = torch.eye(2, dtype=torch.complex64)
+    for bad in [(3,), (-1,), (0, 1)]:
+        with pytest.raises(ValueError):
+            ua.simulation.apply_operator(op, bad, st)
+    with pytest.raises(ValueError):
+        ua.simulation.apply_operator(torch.eye(4, dtype=torch.complex64), (1, 1), st)
+    with pytest.raises(ua.states.StateShapeError):
+        ua.simulation.apply_operator(op, (0,), torch.zeros(6, dtype=torch.complex64))
+    assert issubclass(ua.states.StateShapeError, ValueError)
+    with pytest.raises(RuntimeError):
+        ua.simulation.apply_operator(torch.zeros(3, 3, dtype=torch.complex64), (0,), st)
+    with pytest.raises(ValueError):
+        ua.simulation.apply_all_qubits(torch.eye(4, dtype=torch.complex64), st)
+    with pytest.raises(ValueError):
+        ua.simulation.act_first_qubits(torch.eye(4, dtype=torch.complex64), torch.zeros(2, dtype=torch.complex64))
+
+
+def test_shape_helpers():
+    assert ua.count_qubits(torch.zeros(3, 16)) == 4
+    assert ua.states.count_qubits_gate_matrix(torch.zeros(5, 8, 8)) == 3
+    t = ua.states.to_tensor_layout(torch.arange(24.).reshape(3, 8))
+    assert tuple(t.shape) == (3, 2, 2, 2)
+    assert torch.equal(ua.states.to_vector_layout(t, 3), torch.arange(24.).reshape(3, 8))
+    x = torch.rand(4, 5, 6, 7, 8, 9)
+    assert tuple(ua.states.subset_roll_to_back(x, 2).shape) == (6, 7, 8, 9, 4, 5)
+    assert tuple(ua.states.subset_roll_to_front(x, 2).shape) == (8, 9, 4, 5, 6, 7)
+    # known answers of the reference's test_state_shapes.py (get_qubit_indices doc examples)
+    from unitair_b200.states.shapes import get_qubit_indices
+    assert get_qubit_indices(0, torch.rand(2, 2), num_qubits=2) == 0
+    assert get_qubit_indices(0, torch.rand(500, 17, 2, 2, 2), num_qubits=3) == 2
+    assert get_qubit_indices([1, 0], torch.rand(500, 17, 2, 2, 2), num_qubits=3) == [3, 2]
+    assert get_qubit_indices([-1, 0], torch.rand(500, 17, 2, 2, 2), num_qubits=3) == [-1, 2]
+    from unitair_b200.utils import permutation_to_front, inverse_list_permutation
+    assert permutation_to_front(5, [2]) == [2, 0, 1, 3, 4]
+    assert permutation_to_front(5, [2, 1]) == [2, 1, 0, 3, 4]
+    assert inverse_list_permutation([1, 2, 3, 4, 0]) == [4, 0, 1, 2, 3]
+
+
+def _apply_plan_with_oracle(gates, state, passes):
+    psi = state
+    for p in passes:
+        for g in p.gates:
+            qs, u = gates[g]
+            psi = orc.apply_operator(u, qs, psi)
+    return psi
+
+
+@pytest.mark.parametrize("n,dtype", [(6, torch.complex64), (12, torch.complex64), (14, torch.complex128)])
+def test_pass_planner_preserves_the_circuit(n, dtype):
+    rng = np.random.default_rng(n)
+    gates = []
+    for layer in range(4):
+        for q in range(n):
+            gates.append(([q], rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2))))
+        pi = rng.permutation(n).tolist()
+        for j in range(0, n - 1, 2):
+            gates.append(([pi[j], pi[j + 1]], rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))))
+        gates.append((rng.permutation(n)[:4].tolist(), rng.standard_normal((16, 16)) + 0j))
+    gates = [(qs, (u / np.linalg.norm(u, 2)).astype(np.complex128)) for qs, u in gates]
+    geo = circuit.TileGeometry(n, min(n, 8), min(n, 4), min(n, 8) - min(n, 4))
+    bits = [[n - 1 - q for q in qs] for qs, _ in gates]
+    passes = circuit.plan_passes(bits, geo, max_gates=9)
+    seen = sorted(g for p in passes for g in p.gates)
+    assert seen == list(range(len(gates)))            # every gate exactly once
+    for p in passes:
+        if p.direct:
+            assert len(p.gates) == 1
+            continue
+        assert len(p.gates) <= 9
+        assert len(p.high) == geo.max_high and all(b >= geo.low_bits for b in p.high)
+        tile = set(range(geo.low_bits)) | set(p.high)
+        for g in p.gates:
+            assert set(bits[g]) <= tile
+    state = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    ref = state
+    for qs, u in gates:
+        ref = orc.apply_operator(u, qs, ref)
+    got = _apply_plan_with_oracle(gates, state, passes)
+    assert np.linalg.norm(got - ref) <= 1e-10 * np.linalg.norm(ref)
+    assert len(passes) < len(gates) / 2
+
+
+def test_default_geometry():
+    g = circuit.default_geometry(30, torch.complex64)
+    assert g.tile_bits == 13 and g.low_bits == 7 and g.max_high == 6
+    g = circuit.default_geometry(5, torch.complex64)
+    assert g.tile_bits == 5 and g.low_bits == 5 and g.max_high == 0
+    g = circuit.default_geometry(30, torch.complex128)
+    assert g.tile_bits == 12 and g.low_bits == 6
