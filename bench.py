@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Headline benchmark: gate-amplitude updates/s of a random 1-/2-qubit circuit on a
+30-qubit complex64 state per B200 (weak scaling: 30 + log2(N) qubits sharded over N GPUs by
+the high-order qubits), with the HBM roofline of the dominant kernel and the reference's
+CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" applies the whole `--layers`-layer circuit (SURVEY.md 8d recipe "C2": a Haar
+U(2) on every qubit, then Haar U(4) on the ordered pairs of a random qubit permutation) to
+the state resident in HBM.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "qcware-unitair_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "gate_amplitude_updates_per_s"
+UNIT = "updates/s"
+
+
+# --------------------------------------------------------------------------- workload
+def haar_unitary(rng, dim):
+    z = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    q, r = np.linalg.qr(z)
+    d = np.diagonal(r)
+    return q * (d / np.abs(d))
+
+
+def random_circuit(n, layers, seed):
+    """[(qubits, 2^k x 2^k complex128 ndarray)] -- the C2 layer recipe."""
+    rng = np.random.default_rng(seed)
+    gates = []
+    for _ in range(layers):
+        for q in range(n):
+            gates.append(([q], haar_unitary(rng, 2)))
+        perm = rng.permutation(n).tolist()
+        for j in range(0, n - 1, 2):
+            gates.append(([perm[j], perm[j + 1]], haar_unitary(rng, 4)))
+    return gates
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    out["sm_max_mhz"] = float(parts[1])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), parts[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(kernel):
+    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- reference / CPU arm
+def load_reference():
+    """The unmodified reference if it travelled (baseline/_ref), else the numpy oracle port."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "unitair")):
+        sys.path.insert(0, ref_dir)
+        try:
+            import unitair.simulation as sim  # noqa
+            return "reference", sim
+        except Exception:
+            sys.path.remove(ref_dir)
+    from oracle import unitair_oracle as orc
+    return "port", orc
+
+
+def cpu_layer_rate(n, layers, seed, reps, warm):
+    """gate-amplitude updates/s of the reference's CPU path on an n-qubit sample."""
+    import torch
+    kind, mod = load_reference()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gates = random_circuit(n, layers, seed)
+    if kind == "reference":
+        state = torch.zeros(2 ** n, dtype=torch.complex64)
+        state[0] = 1
+        tg = [(qs, torch.as_tensor(u.astype(np.complex64))) for qs, u in gates]
+
+        def run(psi):
+            for qs, u in tg:
+                psi = mod.apply_operator(operator=u, qubits=qs, state=psi)
+            return psi
+        threads = torch.get_num_threads()
+    else:
+        state = np.zeros(2 ** n, dtype=np.complex64)
+        state[0] = 1
+        tg = [(qs, u.astype(np.complex64)) for qs, u in gates]
+
+        def run(psi):
+            for qs, u in tg:
+                psi = mod.apply_operator(u, qs, psi)
+            return psi
+        threads = 1
+    times = []
+    psi = state
+    for i in range(warm + reps):
+        t0 = time.perf_counter()
+        psi = run(psi)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    updates = len(gates) * float(2 ** n)
+    return {"value": updates / float(np.median(times)), "unit": UNIT, "cores": threads,
+            "kind": kind,
+            "sample": f"{layers} layer(s) of the same recipe ({len(gates)} gates) on a {n}-qubit "
+                      f"complex64 state, median of {reps} after {warm} warm-up, torch CPU threads={threads}"
+            }, float(np.median(times))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_qubits
+    t_all = []
+    base, t_step = cpu_layer_rate(n, 1, args.seed, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_gpus):
+    n_total = args.qubits + int(round(np.log2(n_gpus)))
+    return {
+        "workload": f"random 1-/2-qubit circuit (Haar U(2) on every qubit + Haar U(4) on random "
+                    f"ordered pairs per layer, SURVEY.md 8d C2 recipe), {args.layers} layers, "
+                    f"{n_total}-qubit complex64 state" + (f" sharded over {n_gpus} GPUs by the "
+                    f"{int(round(np.log2(n_gpus)))} highest-order qubits" if n_gpus > 1 else " on 1 GPU"),
+        "qubits": n_total, "qubits_per_gpu": args.qubits, "layers": args.layers,
+        "parallelism": "single GPU" if n_gpus == 1 else f"state sharded over {n_gpus} GPUs (global-qubit swaps)",
+        "l2_policy": f"inputs larger than L2 ({8 * 2 ** args.qubits / 2 ** 30:.0f} GiB state per GPU vs 126 MB L2)",
+    }
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import unitair_b200 as ua
+    from unitair_b200 import _lib, circuit
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    n_local = args.qubits
+    g_bits = int(round(np.log2(world)))
+    assert 2 ** g_bits == world, "--gpus must be a power of two"
+    n_total = n_local + g_bits
+    gates_np = random_circuit(n_total, args.layers, args.seed)
+    gates_dev = [(qs, torch.as_tensor(u.astype(np.complex64)).to(dev)) for qs, u in gates_np]
+    num_gates = len(gates_np)
+    updates_per_step = num_gates * float(2 ** n_total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    result = {}
+    if world == 1:
+        state = torch.zeros(2 ** n_total, dtype=torch.complex64, device=dev)
+        state[0] = 1
+        cc = circuit.CompiledCircuit(gates_dev, n_total, torch.complex64)
+        step = lambda: cc.run(state, in_place=True)   # noqa: E731
+        launches_per_step = cc.num_passes
+        kernel_name = "fused_pass_kernel"
+        extra = {"passes_per_step": cc.num_passes, "gates_per_step": num_gates}
+    else:
+        from unitair_b200 import sharded
+        sstate = sharded.ShardedState.zero_state(n_total, torch.complex64, dev)
+        plan = sharded.ShardedCircuit(gates_dev, n_total, torch.complex64, world)
+        step = lambda: plan.run(sstate)   # noqa: E731
+        launches_per_step = plan.num_passes
+        kernel_name = "fused_pass_kernel"
+        extra = {"passes_per_step": plan.num_passes, "gates_per_step": num_gates,
+                 "swaps_per_step": plan.num_swaps, "swap_bytes_per_gpu_per_step": plan.swap_bytes_per_step}
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - l0
+    elapsed = e0.elapsed_time(e1) / 1e3
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+    value = updates_per_step * args.steps / elapsed
+
+    # roofline of the dominant kernel: algorithmic bytes per launch / average launch time
+    peak, peak_src = measured_hbm_peak()
+    bytes_per_launch = 16.0 * 2 ** n_local                     # read + write of the local state
+    avg_launch_s = elapsed / max(1, launches)
+    achieved = bytes_per_launch / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": recorded_traffic(kernel_name),
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "avg_launch_ms": avg_launch_s * 1e3,
+                "note": "launch time = timed region / native launches" +
+                        ("" if world == 1 else " (includes NVLink swap time)")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64",
+        "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    line.update(extra)
+
+    if world == 1:
+        # ---- per-gate path (the reference's call pattern: one apply_operator per gate) ----
+        psi = state
+        one_layer = gates_dev[: num_gates // args.layers]
+        for qs, u in one_layer[:4]:
+            psi = ua.simulation.apply_operator(u, qs, psi)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0.record()
+        for qs, u in one_layer:
+            psi = ua.simulation.apply_operator(u, qs, psi)
+        e1.record()
+        torch.cuda.synchronize()
+        t_pg = e0.elapsed_time(e1) / 1e3
+        n_pg = _lib.launch_count() - l0
+        ach = bytes_per_launch * n_pg / t_pg / 1e9
+        line["per_gate"] = {
+            "value": len(one_layer) * float(2 ** n_total) / t_pg, "unit": UNIT,
+            "what": "simulation.apply_operator once per gate, one layer, out-of-place",
+            "roofline": {"bound": "hbm", "kernel": "gate_direct_kernel", "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "frac_of_8TBps": ach / 8000.0,
+                         "traffic": recorded_traffic("gate_direct_kernel"),
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "avg_launch_ms": t_pg / n_pg * 1e3}}
+        del psi
+
+        # ---- end to end through the public API with host buffers -------------------------
+        try:
+            h_state = torch.zeros(2 ** n_total, dtype=torch.complex64).pin_memory()
+            h_state[0] = 1
+            h_out = torch.empty(2 ** n_total, dtype=torch.complex64).pin_memory()
+            h_gates = [(qs, torch.as_tensor(u.astype(np.complex64)).pin_memory()) for qs, u in gates_np]
+            gate_bytes = sum(u.numel() * 8 for _, u in h_gates)
+            del state
+            torch.cuda.empty_cache()
+
+            def e2e_step():
+                d_state = h_state.to(dev, non_blocking=True)
+                d_gates = [(qs, u.to(dev, non_blocking=True)) for qs, u in h_gates]
+                out = ua.circuit.apply_gates(d_gates, d_state)
+                h_out.copy_(out, non_blocking=True)
+                return out
+            e2e_step()
+            torch.cuda.synchronize()
+            k_e2e = max(1, min(args.steps, 5))
+            e0.record()
+            for _ in range(k_e2e):
+                e2e_step()
+            e1.record()
+            torch.cuda.synchronize()
+            t_e2e = e0.elapsed_time(e1) / 1e3
+            line["e2e"] = {"value": updates_per_step * k_e2e / t_e2e, "unit": UNIT,
+                           "h2d_bytes_per_step": int(8 * 2 ** n_total + gate_bytes),
+                           "d2h_bytes_per_step": int(8 * 2 ** n_total), "steps": k_e2e,
+                           "ms_per_step": t_e2e / k_e2e * 1e3,
+                           "what": "pinned host state + gates -> device, circuit.apply_gates "
+                                   "(planning + packing inside), final state -> pinned host"}
+            del h_state, h_out
+        except Exception as e:  # pragma: no cover
+            line["e2e"] = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+
+        # ---- CPU baseline (reference's own path on this box's host cores) -----------------
+        if not args.no_cpu_baseline:
+            try:
+                base, _ = cpu_layer_rate(args.cpu_qubits, 1, args.seed, reps=2, warm=1)
+                line["cpu_baseline"] = base
+            except Exception as e:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--qubits", type=int, default=int(os.environ.get("UA_BENCH_QUBITS", 30)),
+                    help="qubits per GPU (the state has qubits + log2(gpus) qubits)")
+    ap.add_argument("--layers", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=202)
+    ap.add_argument("--cpu-qubits", type=int, default=24,
+                    help="size of the bounded CPU sample for the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

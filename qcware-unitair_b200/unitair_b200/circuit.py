@@ -124,43 +124,132 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
 # --------------------------------------------------------------------------- #
 # execution
 # --------------------------------------------------------------------------- #
-def _run_pass(out, inp, n, batch, geo: TileGeometry, p: Pass, gate_bits, offsets, mats,
-              row_stride, adjoint=False):
-    dev = inp.device
-    ks = [len(gate_bits[g]) for g in p.gates]
-    bits_flat = []
-    for g in p.gates:
-        b = list(gate_bits[g])
-        bits_flat += b + [0] * (3 - len(b))
-    offs = [offsets[g] for g in p.gates]
-    low = geo.tile_bits - len(p.high)
-    with L.on_device(dev):
-        L.check(L.lib().ua_apply_fused_pass(
-            L.dtype_code(inp.dtype), out.data_ptr(), inp.data_ptr(), batch << n, n, low,
-            len(p.high), L.int_array(p.high) if p.high else None, len(p.gates),
-            L.int_array(ks), L.int_array(bits_flat), L.ll_array(offs), mats.data_ptr(),
-            row_stride, 1 if adjoint else 0, L.stream_ptr(dev)))
+class _PassLaunch:
+    """Pre-marshalled arguments of one native call (everything except the state pointers)."""
+
+    __slots__ = ("direct", "gate", "low", "nhigh", "high", "ngates", "ks", "bits", "offs")
+
+    def __init__(self, p: Pass, geo: TileGeometry, gate_bits, offsets):
+        self.direct = p.direct
+        self.gate = p.gates[0] if p.direct else -1
+        if p.direct:
+            return
+        self.low = geo.tile_bits - len(p.high)
+        self.nhigh = len(p.high)
+        self.high = L.int_array(p.high) if p.high else None
+        self.ngates = len(p.gates)
+        self.ks = L.int_array([len(gate_bits[g]) for g in p.gates])
+        flat = []
+        for g in p.gates:
+            b = list(gate_bits[g])
+            flat += b + [0] * (3 - len(b))
+        self.bits = L.int_array(flat)
+        self.offs = L.ll_array([offsets[g] for g in p.gates])
 
 
-def _pack_gates(mats_list, batch_shape, dtype, device):
+def _pack_gates(mats_list, batch_shape):
     """One flat device buffer holding every gate matrix; returns (buffer, offsets, row_stride)."""
     offsets = []
     off = 0
     for m in mats_list:
         offsets.append(off)
         off += m.shape[-1] * m.shape[-2]
-    any_batched = any(m.dim() > 2 for m in mats_list)
-    if not any_batched:
-        buf = torch.cat([m.reshape(-1) for m in mats_list])
-        return buf.contiguous(), offsets, 0
-    rows = []
+    if not any(m.dim() > 2 for m in mats_list):
+        return torch.cat([m.reshape(-1) for m in mats_list]).contiguous(), offsets, 0
+    rows = _engine._prod(batch_shape)
+    parts = []
     for m in mats_list:
         if m.dim() == 2:
-            rows.append(m.reshape(1, -1).expand(_engine._prod(batch_shape), -1))
+            parts.append(m.reshape(1, -1).expand(rows, -1))
         else:
-            rows.append(m.expand(tuple(batch_shape) + m.shape[-2:]).reshape(_engine._prod(batch_shape), -1))
-    buf = torch.cat(rows, dim=1).contiguous()
-    return buf, offsets, off
+            parts.append(m.expand(tuple(batch_shape) + m.shape[-2:]).reshape(rows, -1))
+    return torch.cat(parts, dim=1).contiguous(), offsets, off
+
+
+class CompiledCircuit:
+    """An ordered gate list, planned into passes once and replayable on any state of the
+    same shape: `run` only enqueues the native pass kernels (no host planning, no packing).
+
+    gates: sequence of (qubits, operator) with operator (2^k, 2^k) or batch_shape + (2^k, 2^k),
+    complex CUDA tensors of `dtype`.  Gate values are captured at compile time.
+    """
+
+    def __init__(self, gates, num_qubits: int, dtype: torch.dtype, batch_shape=(),
+                 geometry: TileGeometry = None):
+        from . import states
+        n = num_qubits
+        self.n = n
+        self.dtype = dtype
+        self.batch_shape = tuple(batch_shape)
+        self.batch = _engine._prod(self.batch_shape)
+        self.gates = [([int(q) for q in qs], m) for qs, m in gates]
+        for qs, m in self.gates:
+            k = states.count_qubits_gate_matrix(m)
+            if len(qs) != k or len(set(qs)) != k or not set(qs).issubset(range(n)):
+                raise ValueError(f"qubits={qs} is not a valid target list for a {k}-qubit "
+                                 f"operator on {n} qubits")
+            if m.dtype != dtype:
+                raise RuntimeError(f"expected scalar type {dtype} but found {m.dtype}")
+            if m.dim() != 2 and tuple(m.shape[:-2]) != self.batch_shape:
+                raise RuntimeError(f"operator batch dims {tuple(m.shape[:-2])} do not match the "
+                                   f"state batch dims {self.batch_shape}")
+        if self.gates:
+            L.require_cuda(*[m for _, m in self.gates])
+        self.geo = geometry or default_geometry(n, dtype)
+        self.gate_bits = [[n - 1 - q for q in qs] for qs, _ in self.gates]
+        self.passes = plan_passes(self.gate_bits, self.geo) if self.gates else []
+        if self.gates:
+            self.mats, self.offsets, self.row_stride = _pack_gates([m for _, m in self.gates],
+                                                                  self.batch_shape)
+        self.launches = [_PassLaunch(p, self.geo, self.gate_bits, self.offsets) for p in self.passes]
+        self._direct = {}
+        for pl in self.launches:
+            if pl.direct:
+                qs, m = self.gates[pl.gate]
+                self._direct[pl.gate] = (_engine._aligned(m), L.int_array(qs), len(qs),
+                                         0 if m.dim() == 2 else 4 ** len(qs))
+
+    @property
+    def num_gates(self):
+        return len(self.gates)
+
+    @property
+    def num_passes(self):
+        return len(self.launches)
+
+    def run(self, state: torch.Tensor, in_place: bool = False) -> torch.Tensor:
+        """Apply the circuit.  Out-of-place by default (the reference's semantics); with
+        in_place=True the (contiguous, aligned) state buffer is overwritten."""
+        n = self.n
+        if state.dtype != self.dtype or tuple(state.shape) != self.batch_shape + (1 << n,):
+            raise RuntimeError(f"state of size {tuple(state.shape)} / {state.dtype} does not match "
+                               f"the compiled circuit ({self.batch_shape + (1 << n,)}, {self.dtype})")
+        L.require_cuda(state)
+        cur = _engine._aligned(state)
+        if in_place and cur.data_ptr() != state.data_ptr():
+            raise RuntimeError("in_place=True needs a contiguous, 16-byte aligned state")
+        if not self.launches or self.batch == 0:
+            return cur if in_place else cur.clone()
+        dev = cur.device
+        out = cur if in_place else torch.empty_like(cur)
+        src = cur
+        lib = L.lib()
+        code = L.dtype_code(self.dtype)
+        total = self.batch << n
+        with L.on_device(dev):
+            stream = L.stream_ptr(dev)
+            mats_ptr = self.mats.data_ptr()
+            for pl in self.launches:
+                if pl.direct:
+                    m, qarr, k, gstride = self._direct[pl.gate]
+                    L.check(lib.ua_apply_gate(code, out.data_ptr(), src.data_ptr(), m.data_ptr(), n, k,
+                                              qarr, self.batch, 1 << n, gstride, 0, stream))
+                else:
+                    L.check(lib.ua_apply_fused_pass(
+                        code, out.data_ptr(), src.data_ptr(), total, n, pl.low, pl.nhigh, pl.high,
+                        pl.ngates, pl.ks, pl.bits, pl.offs, mats_ptr, self.row_stride, 0, stream))
+                src = out
+        return out
 
 
 def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torch.Tensor,
@@ -169,8 +258,8 @@ def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torc
 
     Equivalent to calling simulation.apply_operator for each gate in turn.  Operators are
     (2^k, 2^k) or share the state's batch dims.  When no gradient is needed the list is
-    executed as fused shared-memory passes; with autograd it falls back to one native
-    gate kernel (and one autograd node) per gate.
+    executed as fused shared-memory passes; with autograd (or broadcasting batch
+    structures) it runs one native gate kernel, and one autograd node, per gate.
     """
     from . import states
     from .simulation import operations as ops
@@ -181,42 +270,14 @@ def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torc
     batch_shape = tuple(state.shape[:-1])
     simple = all(m.dim() == 2 or tuple(m.shape[:-2]) == batch_shape for _, m in gates)
     if needs_grad or not simple or not state.is_complex() or any(m.dtype != state.dtype for _, m in gates):
+        if in_place:
+            raise RuntimeError("in_place=True is not available with autograd or broadcasting gates")
         out = state
         for qs, m in gates:
             out = ops.apply_operator(m, qs, out)
         return out
     L.require_cuda(state, *[m for _, m in gates])
-    for qs, m in gates:
-        k = states.count_qubits_gate_matrix(m)
-        if len(qs) != k or len(set(qs)) != k or not set(qs).issubset(range(n)):
-            raise ValueError(f"qubits={qs} is not a valid target list for a {k}-qubit operator "
-                             f"on {n} qubits")
-    if not gates:
-        return state if in_place else state.clone()
-    batch = _engine._prod(batch_shape)
-    if batch == 0:
-        return state if in_place else state.clone()
-    cur = _engine._aligned(state)
-    if in_place and cur.data_ptr() != state.data_ptr():
-        raise RuntimeError("in_place=True needs a contiguous, 16-byte aligned state")
-    geo = default_geometry(n, state.dtype)
-    gate_bits = [[n - 1 - q for q in qs] for qs, _ in gates]
-    mats, offsets, row_stride = _pack_gates([m for _, m in gates], batch_shape, state.dtype,
-                                            state.device)
-    out = cur if in_place else None
-    for p in plan_passes(gate_bits, geo):
-        src = cur if out is None else out
-        if out is None:
-            out = torch.empty_like(cur)
-        if p.direct:
-            g = p.gates[0]
-            qs, m = gates[g]
-            m_c = _engine._aligned(m)
-            gate_stride = 0 if m.dim() == 2 else 4 ** len(qs)
-            _engine.launch_gate(out, src, m_c, n, len(qs), qs, batch, 1 << n, gate_stride, False)
-        else:
-            _run_pass(out, src, n, batch, geo, p, gate_bits, offsets, mats, row_stride)
-    return out
+    return CompiledCircuit(gates, n, state.dtype, batch_shape).run(state, in_place=in_place)
 
 
 def apply_same_gate_all_qubits(operator: torch.Tensor, state: torch.Tensor, n: int) -> torch.Tensor:

@@ -29,7 +29,7 @@ def ua():
 
 
 def dev(x):
-    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+    return torch.from_numpy(np.array(x, copy=True)).cuda()   # keeps 0-d arrays 0-d
 
 
 def host(t):
