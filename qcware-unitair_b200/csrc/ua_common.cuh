@@ -68,6 +68,37 @@ template <bool STREAM> __device__ __forceinline__ void st16(double2 *p, double2 
     if (STREAM) __stcs(p, v); else *p = v;
 }
 
+// 32-byte (256-bit, sm_100+) accesses: two adjacent 16-byte vectors in one instruction.
+// `p` must be 32-byte aligned.
+template <bool STREAM> __device__ __forceinline__ void ld32(const float4 *p, float4 &a, float4 &b) {
+    if (STREAM)
+        asm volatile("ld.global.cs.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+    else
+        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+template <bool STREAM> __device__ __forceinline__ void ld32(const double2 *p, double2 &a, double2 &b) {
+    if (STREAM)
+        asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+    else
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+template <bool STREAM> __device__ __forceinline__ void st32(float4 *p, const float4 a, const float4 b) {
+    if (STREAM)
+        asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+    else
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+template <bool STREAM> __device__ __forceinline__ void st32(double2 *p, const double2 a, const double2 b) {
+    if (STREAM)
+        asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+    else
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
 static inline bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
 static inline int ilog2(long long x) { int r = 0; while ((1ll << (r + 1)) <= x) ++r; return r; }
 

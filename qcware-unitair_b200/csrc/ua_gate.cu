@@ -30,7 +30,10 @@ struct GateArgs {
     int adjoint;
 };
 
-template <typename R, int K, bool LOW, int U, bool STREAM>
+// PAIR: the lowest vector-level target is vector bit 0, so members v and v|1 of an item are
+// adjacent in memory and move as one 32-byte access (otherwise a warp's 16-byte accesses
+// would be strided by 32 bytes and use half of every sector per instruction).
+template <typename R, int K, bool LOW, int U, bool STREAM, bool PAIR>
 __global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
     using C = typename CplxOf<R>::type;
     using V = typename VecOf<R>::type;
@@ -72,7 +75,11 @@ __global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
 #pragma unroll
                 for (int i = 0; i < KH; ++i)
                     if ((v >> i) & 1) idx |= off[i];
-                x[u][v] = ld16<STREAM>(in + idx);
+                if constexpr (PAIR) {
+                    if ((v & 1) == 0) ld32<STREAM>(in + idx, x[u][v], x[u][v | 1]);
+                } else {
+                    x[u][v] = ld16<STREAM>(in + idx);
+                }
             }
         }
     }
@@ -109,7 +116,10 @@ __global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (!valid[u]) continue;
-#pragma unroll
+        V prev;
+        // K >= 4: keep the row loop rolled, the fully unrolled body (8192 FMAs for K = 5)
+        // overflows the instruction cache (ncu: stall_no_instruction dominated)
+#pragma unroll(K >= 4 ? 1 : NV)
         for (int ov = 0; ov < NV; ++ov) {
             V res;
             if constexpr (APV == 1) {
@@ -141,7 +151,12 @@ __global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
 #pragma unroll
             for (int i = 0; i < KH; ++i)
                 if ((ov >> i) & 1) idx |= off[i];
-            st16<STREAM>(out + idx, res);
+            if constexpr (PAIR) {
+                if (ov & 1) st32<STREAM>(out + (idx ^ 1ull), prev, res);
+                else prev = res;
+            } else {
+                st16<STREAM>(out + idx, res);
+            }
         }
     }
 }
@@ -199,31 +214,41 @@ static int cache_policy() {
     return policy;
 }
 
+struct LaunchOpts { bool low, stream_hint, pair; };
+
 template <typename R, int K, bool LOW, int U>
-static int launch_direct(const GateArgs &a, unsigned grid, bool stream_hint, cudaStream_t st) {
-    if (stream_hint) gate_direct_kernel<R, K, LOW, U, true><<<grid, 256, 0, st>>>(a);
-    else gate_direct_kernel<R, K, LOW, U, false><<<grid, 256, 0, st>>>(a);
+static int launch_direct(const GateArgs &a, unsigned grid, const LaunchOpts &o, cudaStream_t st) {
+    constexpr int KH = LOW ? K - 1 : K;
+    if constexpr (KH >= 1) {
+        if (o.pair) {
+            if (o.stream_hint) gate_direct_kernel<R, K, LOW, U, true, true><<<grid, 256, 0, st>>>(a);
+            else gate_direct_kernel<R, K, LOW, U, false, true><<<grid, 256, 0, st>>>(a);
+            return check_launch("gate_direct_kernel");
+        }
+    }
+    if (o.stream_hint) gate_direct_kernel<R, K, LOW, U, true, false><<<grid, 256, 0, st>>>(a);
+    else gate_direct_kernel<R, K, LOW, U, false, false><<<grid, 256, 0, st>>>(a);
     return check_launch("gate_direct_kernel");
 }
 
 template <typename R, int K, int U>
-static int launch_direct_low(const GateArgs &a, unsigned grid, bool low, bool sh, cudaStream_t st) {
+static int launch_direct_low(const GateArgs &a, unsigned grid, const LaunchOpts &o, cudaStream_t st) {
     if constexpr (VecOf<R>::APV == 2) {
-        if (low) return launch_direct<R, K, true, U>(a, grid, sh, st);
+        if (o.low) return launch_direct<R, K, true, U>(a, grid, o, st);
     }
-    return launch_direct<R, K, false, U>(a, grid, sh, st);
+    return launch_direct<R, K, false, U>(a, grid, o, st);
 }
 
 template <int K> struct UnrollFor { static constexpr int value = K == 1 ? 4 : (K <= 3 ? 2 : 1); };
 
 template <typename R>
-static int dispatch_direct(int k, const GateArgs &a, unsigned grid, bool low, bool sh, cudaStream_t st) {
+static int dispatch_direct(int k, const GateArgs &a, unsigned grid, const LaunchOpts &o, cudaStream_t st) {
     switch (k) {
-        case 1: return launch_direct_low<R, 1, UnrollFor<1>::value>(a, grid, low, sh, st);
-        case 2: return launch_direct_low<R, 2, UnrollFor<2>::value>(a, grid, low, sh, st);
-        case 3: return launch_direct_low<R, 3, UnrollFor<3>::value>(a, grid, low, sh, st);
-        case 4: return launch_direct_low<R, 4, UnrollFor<4>::value>(a, grid, low, sh, st);
-        case 5: return launch_direct_low<R, 5, UnrollFor<5>::value>(a, grid, low, sh, st);
+        case 1: return launch_direct_low<R, 1, UnrollFor<1>::value>(a, grid, o, st);
+        case 2: return launch_direct_low<R, 2, UnrollFor<2>::value>(a, grid, o, st);
+        case 3: return launch_direct_low<R, 3, UnrollFor<3>::value>(a, grid, o, st);
+        case 4: return launch_direct_low<R, 4, UnrollFor<4>::value>(a, grid, o, st);
+        case 5: return launch_direct_low<R, 5, UnrollFor<5>::value>(a, grid, o, st);
     }
     set_error("ua_apply_gate: k=%d out of range", k);
     return UA_ERR_INVALID;
@@ -315,7 +340,13 @@ extern "C" int ua_apply_gate(int dtype, void *out, const void *in, const void *g
 
     const long long bytes = batch * dim * ((dtype == UA_C64) ? 8ll : 16ll);
     const int pol = cache_policy();
-    const bool stream_hint = pol == 1 || (pol == 0 && bytes >= (96ll << 20));
-    if (dtype == UA_C64) return dispatch_direct<float>(k, a, (unsigned)grid, low, stream_hint, st);
-    return dispatch_direct<double>(k, a, (unsigned)grid, low, stream_hint, st);
+    LaunchOpts o;
+    o.low = low;
+    o.stream_hint = pol == 1 || (pol == 0 && bytes >= (96ll << 20));
+    // 32-byte accesses when members v, v|1 are adjacent: needs 32-byte aligned segments
+    const bool aligned32 = !(((uintptr_t)out | (uintptr_t)in) & 31) &&
+                           (flat || ((a.seg_in_stride % 2 == 0) && (a.seg_out_stride % 2 == 0)));
+    o.pair = kh >= 1 && a.vpos[0] == 0 && aligned32;
+    if (dtype == UA_C64) return dispatch_direct<float>(k, a, (unsigned)grid, o, st);
+    return dispatch_direct<double>(k, a, (unsigned)grid, o, st);
 }

@@ -3,12 +3,28 @@
 // (16 B / 32 B per amplitude) for the entire list instead of one per gate.
 //
 // A tile is the set of amplitudes that agree on every index bit outside the tile's T bit
-// positions: the low L bits (contiguous in memory -> 2^L * 8/16 B coalesced runs) plus H
-// chosen higher positions.  Gates whose target bits all lie in that set never need
-// another pass.  This is the engine behind apply_all_qubits
-// (src/unitair/simulation/operations.py:332-413, n strided einsum passes in the reference)
-// and behind the circuit API (the reference's own fusion idea, apply_to_qubits,
-// operations.py:416-503, generalised from same-qubit 2x2 products to whole gate lists).
+// positions: the low L bits (contiguous in memory -> 2^L * 8/16 B runs) plus H chosen
+// higher positions.  Gates whose target bits all lie in that set never need another pass.
+// This is the engine behind apply_all_qubits (src/unitair/simulation/operations.py:332-413,
+// n strided einsum passes in the reference) and behind the circuit API (the reference's own
+// fusion idea, apply_to_qubits, operations.py:416-503, generalised from same-qubit 2x2
+// products to whole gate lists).
+//
+// Kernel structure: persistent CTAs (one per SM), NSTAGE tile buffers in shared memory.
+//   * Tiles move with the bulk asynchronous copy engine (TMA, cp.async.bulk): warp 0 issues
+//     one bulk copy per contiguous run (2^H runs of 2^L amplitudes), completion is tracked
+//     by an mbarrier (global -> shared) or a bulk group (shared -> global).  No registers
+//     are used for staging, and the load of tile i+1 and the store of tile i-1 overlap the
+//     gate phase of tile i.
+//   * Gate phase: each thread takes groups of 2^KH 16-byte vectors (a complex64 target on
+//     local bit 0 lives inside the float4), multiplies by the gate (matrix in shared memory
+//     in register order) and writes the group back, LDS.128/STS.128 throughout.  When a
+//     target sits on one of the three lowest vector bits the 8 lanes of a shared-memory
+//     phase would hit only half/quarter of the banks; those gates take the SWZ path where
+//     lanes read the group members in a lane-dependent order (XOR on the member index) and
+//     undo it with register selects: conflict-free for every target position.
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "ua_common.cuh"
 
 namespace ua {
@@ -33,94 +49,393 @@ struct FusedArgs {
     int high[UA_MAX_TILE_BITS];  // ascending global positions of tile-local bits L..T-1
     int num_gates;
     int adjoint;
+    int nstage;
+    // TMA tensor path: the state seen as a rank-`trank` tensor of 8-byte elements whose
+    // dimension j spans element-index bits [tstart[j], tstart[j+1]); a tile is the box made
+    // of the low bits of every dimension, moved by ONE cp.async.bulk.tensor instruction.
+    int swizzle;                 // 1: bank-conflict-free member swizzle for low targets
+    int trank;                   // 0 = tensor path off (per-run bulk copies instead)
+    int tstart[6];
+    alignas(64) CUtensorMap tmap_in;
+    alignas(64) CUtensorMap tmap_out;
     FusedGate gates[UA_MAX_FUSED_GATES];
 };
 
 constexpr int FUSED_MAX_MAT_ELEMS = 2048;   // complex elements of gate matrices per pass
 
-template <typename R, int K>
-__device__ __forceinline__ void apply_gate_smem(typename CplxOf<R>::type *tile,
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src_gmem, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, unsigned src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load(int rank, unsigned dst, const CUtensorMap *tm, const int *c, unsigned bar) {
+    const unsigned long long t = reinterpret_cast<unsigned long long>(tm);
+    switch (rank) {
+        case 1: asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2}], [%3];"
+                             ::"r"(dst), "l"(t), "r"(c[0]), "r"(bar) : "memory"); break;
+        case 2: asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(dst), "l"(t), "r"(c[0]), "r"(c[1]), "r"(bar) : "memory"); break;
+        case 3: asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(dst), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(bar) : "memory"); break;
+        case 4: asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                             ::"r"(dst), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(bar) : "memory"); break;
+        default: asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                             ::"r"(dst), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(bar) : "memory"); break;
+    }
+}
+__device__ __forceinline__ void tma_store(int rank, const CUtensorMap *tm, const int *c, unsigned src) {
+    const unsigned long long t = reinterpret_cast<unsigned long long>(tm);
+    switch (rank) {
+        case 1: asm volatile("cp.async.bulk.tensor.1d.global.shared::cta.tile.bulk_group [%0, {%1}], [%2];"
+                             ::"l"(t), "r"(c[0]), "r"(src) : "memory"); break;
+        case 2: asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(src) : "memory"); break;
+        case 3: asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                             ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(src) : "memory"); break;
+        case 4: asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                             ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(src) : "memory"); break;
+        default: asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
+                             ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(src) : "memory"); break;
+    }
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ unsigned insert_zero32(unsigned x, int p) {
+    const unsigned lo = x & ((1u << p) - 1u);
+    return ((x >> p) << (p + 1)) | lo;
+}
+
+template <typename V> __device__ __forceinline__ void cond_swap(V &a, V &b, bool doit) {
+    const V ta = a, tb = b;
+    a = doit ? tb : ta;
+    b = doit ? ta : tb;
+}
+
+// One gate on the whole tile.  K qubits; LOW: (complex64 only) the lowest target is local
+// bit 0, i.e. inside the float4; SWZ: some vector-level target is among the 3 lowest vector
+// bits (bank-conflict avoiding member swizzle on).  `tv` is the tile as 16-byte vectors,
+// TV = log2 of their count.  GU groups are processed together for memory-level parallelism.
+template <typename R, int K, bool LOW, bool SWZ>
+__device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
                                                 const typename CplxOf<R>::type *M,
-                                                const FusedGate &gd, int T, int nthreads) {
+                                                const FusedGate &gd, int TV, int nthreads) {
     using C = typename CplxOf<R>::type;
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    constexpr int APVLOG = APV == 2 ? 1 : 0;
+    constexpr int KH = LOW ? K - 1 : K;
+    constexpr int NV = 1 << KH;
     constexpr int D = 1 << K;
-    unsigned off[K];
+    constexpr int INFLIGHT = sizeof(R) == 4 ? 4 : 2;  // 16-byte vectors in flight per thread
+    constexpr int GU = (K >= 2 || NV >= INFLIGHT) ? 1 : INFLIGHT / NV;   // K >= 2: the matrix fills the registers
+
+    int vb[KH > 0 ? KH : 1];          // ascending vector-bit positions of the vector-level targets
+    unsigned off[KH > 0 ? KH : 1];
+    int m = 0;                        // how many of them are among the 3 lowest vector bits
 #pragma unroll
-    for (int i = 0; i < K; ++i) off[i] = 1u << gd.sb[i];
+    for (int i = 0; i < KH; ++i) {
+        vb[i] = (int)gd.sb[i + (LOW ? 1 : 0)] - APVLOG;
+        off[i] = 1u << vb[i];
+        m += (vb[i] < 3) ? 1 : 0;
+    }
+    unsigned msk = 0;
+    if (SWZ) {
+        // lane-dependent member swizzle: low target i is selected by lane bit (3 - m + i)
+        const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+        for (int i = 0; i < KH; ++i)
+            if (i < m) msk |= ((lane >> (3 - m + i)) & 1u) << i;
+    }
+
     constexpr bool MREG = (K <= 2);
     C mr[MREG ? D * D : 1];
     if (MREG) {
 #pragma unroll
         for (int e = 0; e < D * D; ++e) mr[e] = M[e];
     }
-    const unsigned groups = 1u << (T - K);
-    for (unsigned g = threadIdx.x; g < groups; g += nthreads) {
-        unsigned b = g;
+    auto Mat = [&](int s, int t) -> C { return MREG ? mr[s * D + t] : M[s * D + t]; };
+
+    const unsigned groups = 1u << (TV - KH);
+    for (unsigned g0 = threadIdx.x; g0 < groups; g0 += nthreads * GU) {
+        unsigned gbase[GU];
+        V x[GU][NV];
+        bool ok[GU];
 #pragma unroll
-        for (int i = 0; i < K; ++i) b = (unsigned)insert_zero(b, gd.sb[i]);
-        C x[D];
+        for (int u = 0; u < GU; ++u) {
+            const unsigned g = g0 + u * nthreads;
+            ok[u] = g < groups;
+            unsigned b = g;
 #pragma unroll
-        for (int s = 0; s < D; ++s) {
-            unsigned idx = b;
+            for (int i = 0; i < KH; ++i) b = insert_zero32(b, vb[i]);
+            gbase[u] = b;
 #pragma unroll
-            for (int i = 0; i < K; ++i)
-                if ((s >> i) & 1) idx |= off[i];
-            x[s] = tile[idx];
+            for (int c = 0; c < NV; ++c) {
+                const unsigned cc = SWZ ? ((unsigned)c ^ msk) : (unsigned)c;
+                unsigned idx = b;
+#pragma unroll
+                for (int i = 0; i < KH; ++i)
+                    if ((cc >> i) & 1u) idx |= off[i];
+                if (ok[u]) x[u][c] = tv[idx];
+            }
         }
 #pragma unroll
-        for (int s = 0; s < D; ++s) {
-            C acc = mk(R(0), R(0));
+        for (int u = 0; u < GU; ++u) {
+            if (!ok[u]) continue;
+            if (SWZ) {   // undo the swizzle: x[c] currently holds member (c ^ msk)
 #pragma unroll
-            for (int t = 0; t < D; ++t) cfma(acc, MREG ? mr[s * D + t] : M[s * D + t], x[t]);
-            unsigned idx = b;
+                for (int i = 0; i < KH; ++i) {
+                    const bool sw = (msk >> i) & 1u;
 #pragma unroll
-            for (int i = 0; i < K; ++i)
-                if ((s >> i) & 1) idx |= off[i];
-            tile[idx] = acc;
+                    for (int c = 0; c < NV; ++c)
+                        if (!((c >> i) & 1)) cond_swap(x[u][c], x[u][c | (1 << i)], sw);
+                }
+            }
+            V y[SWZ ? NV : 1];
+#pragma unroll
+            for (int ov = 0; ov < NV; ++ov) {
+                V res;
+                if constexpr (APV == 1) {
+                    C acc = mk(R(0), R(0));
+#pragma unroll
+                    for (int t = 0; t < D; ++t) cfma(acc, Mat(ov, t), x[u][t]);
+                    res = acc;
+                } else if constexpr (LOW) {
+                    C acc0 = mk(R(0), R(0)), acc1 = mk(R(0), R(0));
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        const V xv = x[u][t >> 1];
+                        const C amp = (t & 1) ? mk(xv.z, xv.w) : mk(xv.x, xv.y);
+                        cfma(acc0, Mat(2 * ov, t), amp);
+                        cfma(acc1, Mat(2 * ov + 1, t), amp);
+                    }
+                    res = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
+                } else {
+                    C acc0 = mk(R(0), R(0)), acc1 = mk(R(0), R(0));
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        const C gm = Mat(ov, t);
+                        cfma(acc0, gm, mk(x[u][t].x, x[u][t].y));
+                        cfma(acc1, gm, mk(x[u][t].z, x[u][t].w));
+                    }
+                    res = make_float4(acc0.x, acc0.y, acc1.x, acc1.y);
+                }
+                if constexpr (SWZ) {
+                    y[ov] = res;
+                } else {       // every member is already in registers: store right away
+                    unsigned idx = gbase[u];
+#pragma unroll
+                    for (int i = 0; i < KH; ++i)
+                        if ((ov >> i) & 1) idx |= off[i];
+                    tv[idx] = res;
+                }
+            }
+            if constexpr (SWZ) {   // y[c] must become member (c ^ msk) again for the store slots
+#pragma unroll
+                for (int i = 0; i < KH; ++i) {
+                    const bool sw = (msk >> i) & 1u;
+#pragma unroll
+                    for (int c = 0; c < NV; ++c)
+                        if (!((c >> i) & 1)) cond_swap(y[c], y[c | (1 << i)], sw);
+                }
+#pragma unroll
+                for (int c = 0; c < NV; ++c) {
+                    const unsigned cc = (unsigned)c ^ msk;
+                    unsigned idx = gbase[u];
+#pragma unroll
+                    for (int i = 0; i < KH; ++i)
+                        if ((cc >> i) & 1u) idx |= off[i];
+                    tv[idx] = y[c];
+                }
+            }
         }
     }
 }
 
-template <typename R, int THREADS>
-__global__ void __launch_bounds__(THREADS) fused_pass_kernel(const __grid_constant__ FusedArgs a) {
+template <typename R, int K, bool LOW>
+__device__ __forceinline__ void apply_gate_swz(typename VecOf<R>::type *tv,
+                                               const typename CplxOf<R>::type *M,
+                                               const FusedGate &gd, int TV, int nthreads, bool allow_swz) {
+    constexpr int APVLOG = VecOf<R>::APV == 2 ? 1 : 0;
+    constexpr int KH = LOW ? K - 1 : K;
+    bool swz = false;
+    if constexpr (KH > 0) swz = allow_swz && ((int)gd.sb[LOW ? 1 : 0] - APVLOG) < 3;   // lowest vector-level target
+    if constexpr (KH > 0 && K <= 2) {   // 3-qubit gates (rare after merging) keep the plain path
+        if (swz) { apply_gate_smem<R, K, LOW, true>(tv, M, gd, TV, nthreads); return; }
+    }
+    apply_gate_smem<R, K, LOW, false>(tv, M, gd, TV, nthreads);
+}
+
+template <typename R>
+__device__ __forceinline__ void apply_any_gate(typename VecOf<R>::type *tv,
+                                               const typename CplxOf<R>::type *M,
+                                               const FusedGate &gd, int TV, int nthreads, bool swz) {
+    constexpr int APV = VecOf<R>::APV;
+    if constexpr (APV == 2) {
+        if (gd.sb[0] == 0) {
+            if (gd.k == 1) apply_gate_swz<R, 1, true>(tv, M, gd, TV, nthreads, swz);
+            else if (gd.k == 2) apply_gate_swz<R, 2, true>(tv, M, gd, TV, nthreads, swz);
+            else apply_gate_swz<R, 3, true>(tv, M, gd, TV, nthreads, swz);
+            return;
+        }
+    }
+    if (gd.k == 1) apply_gate_swz<R, 1, false>(tv, M, gd, TV, nthreads, swz);
+    else if (gd.k == 2) apply_gate_swz<R, 2, false>(tv, M, gd, TV, nthreads, swz);
+    else apply_gate_swz<R, 3, false>(tv, M, gd, TV, nthreads, swz);
+}
+
+// Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  Shared memory layout:
+// [nstage tile buffers][gate matrices]; mbarriers are static.
+template <typename R, int FUSED_THREADS>
+__global__ void __launch_bounds__(FUSED_THREADS, 512 / FUSED_THREADS) fused_pass_kernel(const __grid_constant__ FusedArgs a) {
     using C = typename CplxOf<R>::type;
     using V = typename VecOf<R>::type;
-    constexpr int APV = VecOf<R>::APV;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *tile = reinterpret_cast<C *>(smem_raw);
-    C *sM = tile + (1u << a.T);
-    const unsigned nvec = (1u << a.T) / APV;
-    const unsigned lowmask = (1u << a.L) - 1u;
+    constexpr int APVLOG = VecOf<R>::APV == 2 ? 1 : 0;
+    constexpr int MAXSTAGE = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[MAXSTAGE];
 
-    bool mats_loaded = false;
-    for (long long tile_id = blockIdx.x; tile_id < a.num_tiles; tile_id += gridDim.x) {
-        const long long row = tile_id / a.tiles_per_row;
+    const unsigned tile_bytes = (1u << a.T) * (unsigned)sizeof(C);
+    const int nstage = a.nstage;
+    C *sM = reinterpret_cast<C *>(smem_raw + (size_t)nstage * tile_bytes);
+    const int TV = a.T - APVLOG;
+    const unsigned run_bytes = (1u << a.L) * (unsigned)sizeof(C);
+    const unsigned runs = 1u << a.H;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool mover = threadIdx.x < 32;      // warp 0 drives the copy engine
+    const char *in = reinterpret_cast<const char *>(a.in);
+    char *out = reinterpret_cast<char *>(a.out);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < nstage; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncthreads();
+
+    auto tile_base = [&](long long tile_id, long long &row) -> uint64_t {
+        row = tile_id / a.tiles_per_row;
         const long long j = tile_id - row * a.tiles_per_row;
         uint64_t base = (uint64_t)j << a.L;
         for (int i = 0; i < a.H; ++i) base = insert_zero(base, a.high[i]);
-        base += (uint64_t)row << a.total_bits;
-
-        // ---- tile loads first (coalesced 2^L-amplitude runs) -------------------------
-        const V *__restrict__ in = reinterpret_cast<const V *>(a.in);
-        for (unsigned v = threadIdx.x; v < nvec; v += THREADS) {
-            const unsigned la = v * APV;
-            uint64_t idx = base + (la & lowmask);
-            const unsigned hi = la >> a.L;
-            for (int i = 0; i < a.H; ++i)
-                if ((hi >> i) & 1) idx |= 1ull << a.high[i];
-            reinterpret_cast<V *>(tile)[v] = __ldcs(in + idx / APV);
+        return base + ((uint64_t)row << a.total_bits);
+    };
+    auto run_offset = [&](unsigned r) -> uint64_t {   // amplitude offset of run r inside a tile
+        uint64_t o = 0;
+        for (int i = 0; i < a.H; ++i)
+            if ((r >> i) & 1u) o |= 1ull << a.high[i];
+        return o;
+    };
+    constexpr int EBITS = sizeof(C) == 8 ? 0 : 1;    // 8-byte TMA elements per amplitude (log2)
+    auto tensor_coords = [&](uint64_t base, int *c) {
+        const uint64_t e = base << EBITS;
+        for (int j = 0; j < a.trank; ++j) {
+            uint64_t v = e >> a.tstart[j];
+            if (j + 1 < a.trank) v &= (1ull << (a.tstart[j + 1] - a.tstart[j])) - 1ull;
+            c[j] = (int)v;
         }
-        // ---- gate matrices -> shared memory, register order ---------------------------
+    };
+    auto issue_load = [&](long long tile_id, int s) {   // warp 0 only
+        long long row;
+        const uint64_t base = tile_base(tile_id, row);
+        const unsigned bar = smem_u32(&bars[s]);
+        if (lane == 0) mbar_arrive_expect_tx(bar, tile_bytes);
+        __syncwarp();
+        const unsigned dst = smem_u32(smem_raw + (size_t)s * tile_bytes);
+        if (a.trank > 0) {
+            if (lane == 0) {
+                int c[5];
+                tensor_coords(base, c);
+                tma_load(a.trank, dst, &a.tmap_in, c, bar);
+            }
+        } else {
+            for (unsigned r = lane; r < runs; r += 32)
+                bulk_g2s(dst + r * run_bytes, in + (base + run_offset(r)) * sizeof(C), run_bytes, bar);
+        }
+    };
+    auto issue_store = [&](long long tile_id, int s) {  // warp 0 only
+        long long row;
+        const uint64_t base = tile_base(tile_id, row);
+        const unsigned src = smem_u32(smem_raw + (size_t)s * tile_bytes);
+        if (a.trank > 0) {
+            if (lane == 0) {
+                int c[5];
+                tensor_coords(base, c);
+                tma_store(a.trank, &a.tmap_out, c, src);
+            }
+        } else {
+            for (unsigned r = lane; r < runs; r += 32)
+                bulk_s2g(out + (base + run_offset(r)) * sizeof(C), src + r * run_bytes, run_bytes);
+        }
+        bulk_commit();
+    };
+
+    const long long first = blockIdx.x;
+    const long long step = gridDim.x;
+    // prologue: fill nstage-1 stages
+    if (mover) {
+        for (int p = 0; p < nstage - 1; ++p) {
+            const long long t = first + p * step;
+            if (t < a.num_tiles) issue_load(t, p);
+        }
+    }
+
+    bool mats_loaded = false;
+    long long it = 0;
+    for (long long tile_id = first; tile_id < a.num_tiles; tile_id += step, ++it) {
+        const int s = (int)(it % nstage);
+        const unsigned parity = (unsigned)((it / nstage) & 1);
+        // prefetch tile it+nstage-1 into the stage that tile it-1 used (its store was issued
+        // at the end of the previous iteration: wait until the engine has read it)
+        if (mover) {
+            const long long tn = tile_id + (long long)(nstage - 1) * step;
+            if (tn < a.num_tiles) {
+                bulk_wait_read_all();
+                __syncwarp();
+                issue_load(tn, (int)((it + nstage - 1) % nstage));
+            }
+        }
+        // gate matrices -> shared memory, register order (once, or per row for batched gates)
         if (!mats_loaded || a.mats_row_stride != 0) {
+            const long long row = tile_id / a.tiles_per_row;
             const C *__restrict__ mats = reinterpret_cast<const C *>(a.mats) + row * a.mats_row_stride;
+            if (mats_loaded) __syncthreads();          // previous tile's gates are done with sM
             for (int g = 0; g < a.num_gates; ++g) {
                 const FusedGate &gd = a.gates[g];
                 const int K = gd.k, D = 1 << K;
-                for (int e = threadIdx.x; e < D * D; e += THREADS) {
-                    const int s = e >> K, t = e & (D - 1);
+                for (int e = threadIdx.x; e < D * D; e += FUSED_THREADS) {
+                    const int sr = e >> K, t = e & (D - 1);
                     int gi = 0, gj = 0;
                     for (int i = 0; i < K; ++i) {
-                        gi |= ((s >> i) & 1) << gd.gb[i];
+                        gi |= ((sr >> i) & 1) << gd.gb[i];
                         gj |= ((t >> i) & 1) << gd.gb[i];
                     }
                     C val;
@@ -130,53 +445,122 @@ __global__ void __launch_bounds__(THREADS) fused_pass_kernel(const __grid_consta
                 }
             }
             mats_loaded = true;
-        }
-        __syncthreads();
-
-        // ---- all gates in shared memory ------------------------------------------------
-        for (int g = 0; g < a.num_gates; ++g) {
-            const FusedGate &gd = a.gates[g];
-            const C *M = sM + gd.smoff;
-            if (gd.k == 1) apply_gate_smem<R, 1>(tile, M, gd, a.T, THREADS);
-            else if (gd.k == 2) apply_gate_smem<R, 2>(tile, M, gd, a.T, THREADS);
-            else apply_gate_smem<R, 3>(tile, M, gd, a.T, THREADS);
             __syncthreads();
         }
+        mbar_wait(smem_u32(&bars[s]), parity);
 
-        // ---- write back ------------------------------------------------------------------
-        V *out = reinterpret_cast<V *>(a.out);
-        for (unsigned v = threadIdx.x; v < nvec; v += THREADS) {
-            const unsigned la = v * APV;
-            uint64_t idx = base + (la & lowmask);
-            const unsigned hi = la >> a.L;
-            for (int i = 0; i < a.H; ++i)
-                if ((hi >> i) & 1) idx |= 1ull << a.high[i];
-            __stcs(out + idx / APV, reinterpret_cast<V *>(tile)[v]);
+        V *tv = reinterpret_cast<V *>(smem_raw + (size_t)s * tile_bytes);
+        for (int g = 0; g < a.num_gates; ++g) {
+            const FusedGate &gd = a.gates[g];
+            apply_any_gate<R>(tv, sM + gd.smoff, gd, TV, FUSED_THREADS, a.swizzle != 0);
+            if (g + 1 < a.num_gates) __syncthreads();
         }
-        __syncthreads();   // tile buffer is reused by the next iteration
+        fence_proxy_async();        // make the generic-proxy writes visible to the copy engine
+        __syncthreads();
+        if (mover) issue_store(tile_id, s);
     }
+    if (mover) bulk_wait_all();
 }
 
 static int max_tile_bits(int dtype) { return dtype == UA_C64 ? 14 : 13; }
 
-template <typename R, int THREADS>
-static int launch_fused(const FusedArgs &a, size_t smem, cudaStream_t st) {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// Describe the tile set {0..L-1} U high[] (amplitude bits) as TMA boxes.  Works in 8-byte
+// element bits (complex128 = 2 elements).  Returns false when more than 5 dimensions would be
+// needed or the encoder is unavailable; the kernel then moves tiles run by run.
+static bool setup_tensor_maps(FusedArgs &a, int ebits, long long total_amps) {
+    if (getenv("UA_FUSED_NO_TENSOR")) return false;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    // windows of consecutive element bits inside the tile, each at most 8 bits (box <= 256)
+    int wstart[16], wlen[16], nw = 0;
+    int pos[UA_MAX_TILE_BITS + 2], np = 0;
+    for (int b = 0; b < a.L + ebits; ++b) pos[np++] = b;
+    for (int i = 0; i < a.H; ++i) pos[np++] = a.high[i] + ebits;
+    for (int i = 0; i < np; ++i) {
+        if (nw > 0 && pos[i] == wstart[nw - 1] + wlen[nw - 1] && wlen[nw - 1] < 8) wlen[nw - 1]++;
+        else { if (nw == 16) return false; wstart[nw] = pos[i]; wlen[nw] = 1; nw++; }
+    }
+    if (nw > 5) return false;
+    const unsigned long long total_elems = (unsigned long long)total_amps << ebits;
+    cuuint64_t gdim[5], gstride[4];
+    cuuint32_t box[5], estr[5];
+    for (int j = 0; j < nw; ++j) {
+        a.tstart[j] = wstart[j];
+        box[j] = 1u << wlen[j];
+        estr[j] = 1;
+        if (j + 1 < nw) gdim[j] = 1ull << (wstart[j + 1] - wstart[j]);
+        else gdim[j] = total_elems >> wstart[j];
+        if (gdim[j] > 0xffffffffull || gdim[j] < box[j]) return false;
+        if (j > 0) gstride[j - 1] = (8ull << wstart[j]);
+    }
+    a.tstart[nw] = 0;
+    for (int which = 0; which < 2; ++which) {
+        void *addr = const_cast<void *>(which == 0 ? a.in : (const void *)a.out);
+        CUtensorMap *tm = which == 0 ? &a.tmap_in : &a.tmap_out;
+        const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)nw, addr, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
+    a.trank = nw;
+    return true;
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <typename R, int FUSED_THREADS>
+static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = fused_pass_kernel<R, THREADS>;
+    auto kern = fused_pass_kernel<R, FUSED_THREADS>;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { set_error("ua_apply_fused_pass: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return UA_ERR_CUDA; }
         attr_set = true;
     }
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem);
-    if (e != cudaSuccess || per_sm < 1) { set_error("ua_apply_fused_pass: occupancy query failed (%s), smem=%zu", cudaGetErrorString(e), smem); cudaGetLastError(); return UA_ERR_CUDA; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // shared memory budget per CTA: 512/FUSED_THREADS CTAs share an SM
+    const int ctas = 512 / FUSED_THREADS;
+    const size_t budget = (size_t)(224 * 1024) / ctas - 1024;
+    int nstage = (budget > mat_bytes) ? (int)((budget - mat_bytes) / tile_bytes) : 0;
+    if (nstage > 3) nstage = 3;
+    if (nstage < 1) { set_error("ua_apply_fused_pass: tile does not fit in shared memory"); return UA_ERR_UNSUPPORTED; }
+    const int want = env_int("UA_FUSED_STAGES", 0);
+    if (want >= 1 && want <= nstage) nstage = want;
+    a.nstage = nstage;
+    a.swizzle = env_int("UA_FUSED_SWZ", 0);
+    const size_t smem = (size_t)nstage * tile_bytes + mat_bytes;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, smem);
+    if (e != cudaSuccess || per_sm < 1) { set_error("ua_apply_fused_pass: occupancy query failed (%s), smem=%zu", cudaGetErrorString(e), smem); cudaGetLastError(); return UA_ERR_CUDA; }
     long long grid = (long long)per_sm * sms;
     if (grid > a.num_tiles) grid = a.num_tiles;
-    kern<<<(unsigned)grid, THREADS, smem, st>>>(a);
+    kern<<<(unsigned)grid, FUSED_THREADS, smem, st>>>(a);
     return check_launch("fused_pass_kernel");
 }
 
@@ -232,6 +616,7 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     for (int g = 0; g < num_gates; ++g) {
         const int k = host_gate_k[g];
         if (k < 1 || k > 3) { set_error("ua_apply_fused_pass: gate %d has k=%d (1..3 supported)", g, k); return UA_ERR_UNSUPPORTED; }
+        if (k > T) { set_error("ua_apply_fused_pass: gate %d has more qubits than the tile", g); return UA_ERR_INVALID; }
         FusedGate &gd = a.gates[g];
         gd.k = (unsigned char)k;
         gd.goff = host_gate_offset[g];
@@ -250,14 +635,19 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     }
     if (mat_elems > FUSED_MAX_MAT_ELEMS) { set_error("ua_apply_fused_pass: %d matrix elements exceed the %d limit", mat_elems, FUSED_MAX_MAT_ELEMS); return UA_ERR_INVALID; }
 
+    a.trank = 0;
+    setup_tensor_maps(a, dtype == UA_C64 ? 0 : 1, total_amps);
     const size_t csize = (dtype == UA_C64) ? 8 : 16;
-    const size_t smem = ((size_t)(1u << T) + (size_t)mat_elems) * csize;
+    const size_t tile_bytes = ((size_t)1 << T) * csize;
+    const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
+    // 256-thread CTAs run two per SM (phases of the two interleave); fall back to one
+    // 512-thread CTA when two tiles do not fit
+    int threads = env_int("UA_FUSED_THREADS", 256);
+    if (threads == 256 && 2 * (tile_bytes + mat_bytes) > (size_t)222 * 1024) threads = 512;
     if (dtype == UA_C64) {
-        if (T <= 12) return launch_fused<float, 256>(a, smem, st);
-        if (T == 13) return launch_fused<float, 512>(a, smem, st);
-        return launch_fused<float, 1024>(a, smem, st);
+        if (threads == 256) return launch_fused<float, 256>(a, tile_bytes, mat_bytes, st);
+        return launch_fused<float, 512>(a, tile_bytes, mat_bytes, st);
     }
-    if (T <= 11) return launch_fused<double, 256>(a, smem, st);
-    if (T == 12) return launch_fused<double, 512>(a, smem, st);
-    return launch_fused<double, 1024>(a, smem, st);
+    if (threads == 256) return launch_fused<double, 256>(a, tile_bytes, mat_bytes, st);
+    return launch_fused<double, 512>(a, tile_bytes, mat_bytes, st);
 }

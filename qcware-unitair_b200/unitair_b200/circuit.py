@@ -35,6 +35,28 @@ class TileGeometry:
     tile_bits: int       # T
     low_bits: int        # L: always-resident contiguous low bits
     max_high: int        # H = T - L
+    elem_bits: int = 0   # log2(8-byte TMA elements per amplitude): 0 complex64, 1 complex128
+    max_windows: int = 5  # TMA tensor rank limit (see count_windows)
+
+
+def count_windows(low_bits: int, high, elem_bits: int = 0) -> int:
+    """Number of TMA box dimensions needed for the tile {0..low_bits-1} U high.
+
+    A dimension covers a run of consecutive (8-byte element) index bits, at most 8 of them
+    (box extent <= 256).  Mirrors setup_tensor_maps() in csrc/ua_tile.cu: with at most 5
+    dimensions a tile moves with ONE cp.async.bulk.tensor instruction, otherwise the kernel
+    falls back to one bulk copy per contiguous run (much slower to issue).
+    """
+    pos = list(range(low_bits + elem_bits)) + [h + elem_bits for h in sorted(high)]
+    n = 0
+    start = length = None
+    for b in pos:
+        if n and b == start + length and length < 8:
+            length += 1
+        else:
+            n += 1
+            start, length = b, 1
+    return n
 
 
 @dataclass
@@ -52,14 +74,14 @@ def default_geometry(num_qubits: int, dtype: torch.dtype) -> TileGeometry:
     every global access a coalesced 1 KiB run.
     """
     if dtype == torch.complex128:
-        tile, low = 12, 6
+        tile, low, ebits = 12, 6, 1
     else:
-        tile, low = 13, 7
+        tile, low, ebits = 13, 7, 0
     tile = int(os.environ.get("UA_TILE_BITS", tile))
     low = int(os.environ.get("UA_TILE_LOW_BITS", low))
     tile = min(tile, num_qubits)
     low = min(low, tile)
-    return TileGeometry(num_qubits, tile, low, tile - low)
+    return TileGeometry(num_qubits, tile, low, tile - low, ebits)
 
 
 def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
@@ -101,7 +123,8 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
                 blocked.update(bits)
                 continue
             need = {b for b in bits if b >= geo.low_bits} - high
-            if len(high) + len(need) > geo.max_high or mat_elems + 4 ** k > max_mat_elems:
+            if (len(high) + len(need) > geo.max_high or mat_elems + 4 ** k > max_mat_elems
+                    or (need and count_windows(geo.low_bits, high | need, geo.elem_bits) > geo.max_windows)):
                 blocked.update(bits)
                 continue
             high |= need
@@ -110,15 +133,88 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             done[g] = True
             if len(blocked) >= geo.total_bits:
                 break
-        # fill the unused high slots with the lowest free positions so the tile is full
-        p = geo.low_bits
-        while len(high) < geo.max_high and p < geo.total_bits:
-            if p not in high:
-                high.add(p)
-            p += 1
+        # fill the unused high slots so the tile is full: first positions that keep the number
+        # of TMA dimensions (extend an existing run), then anything
+        while len(high) < geo.max_high:
+            free = [p for p in range(geo.low_bits, geo.total_bits) if p not in high]
+            if not free:
+                break
+            best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits), p))
+            high.add(best)
         cur.high = sorted(high)
         passes.append(cur)
     return passes
+
+
+# --------------------------------------------------------------------------- #
+# gate merging (host bookkeeping + tiny device matmuls, no synchronisation)
+# --------------------------------------------------------------------------- #
+_SWAP_IDX = [0, 2, 1, 3]
+
+
+def _lift_to_pair(qs, m, pair):
+    """Matrix of the 1- or 2-qubit gate (qs, m) as a 4x4 on the ordered `pair`."""
+    if len(qs) == 2:
+        if list(qs) == list(pair):
+            return m
+        idx = torch.tensor(_SWAP_IDX, device=m.device)
+        return m.index_select(-2, idx).index_select(-1, idx)
+    eye = torch.eye(2, dtype=m.dtype, device=m.device)
+    if qs[0] == pair[0]:
+        return _bkron(m, eye)
+    return _bkron(eye, m)
+
+
+def _bkron(a, b):
+    """Kronecker product over the last two dims with broadcasting batch dims."""
+    a4 = a.unsqueeze(-1).unsqueeze(-3)          # (..., i, 1, j, 1)
+    b4 = b.unsqueeze(-2).unsqueeze(-4)          # (..., 1, k, 1, l)
+    out = a4 * b4
+    return out.reshape(out.shape[:-4] + (out.shape[-4] * out.shape[-3], out.shape[-2] * out.shape[-1]))
+
+
+def merge_gates(gates):
+    """Merge neighbouring 1-/2-qubit gates into at most 2-qubit blocks.
+
+    * a gate whose qubits are all covered by the most recent block on those qubits is
+      multiplied into that block;
+    * a 2-qubit gate absorbs pending 1-qubit blocks on its qubits.
+    Gates on 3+ qubits are kept as they are.  Only gates acting on disjoint qubits are
+    commuted, so the product is unchanged.  Returns a new [(qubits, matrix)] list.
+    """
+    blocks = []          # [qubits, matrix] or None when absorbed
+    last = {}            # qubit -> index of the most recent block touching it
+    for qs, m in gates:
+        qs = list(qs)
+        k = len(qs)
+        if k > 2:
+            blocks.append([qs, m])
+            for q in qs:
+                last[q] = len(blocks) - 1
+            continue
+        owners = {last.get(q) for q in qs}
+        if len(owners) == 1 and None not in owners:
+            bi = owners.pop()
+            bq, bm = blocks[bi]
+            if len(bq) <= 2 and set(qs) <= set(bq):
+                if len(bq) == 1:
+                    blocks[bi][1] = torch.matmul(m, bm)
+                else:
+                    blocks[bi][1] = torch.matmul(_lift_to_pair(qs, m, bq), bm)
+                continue
+        if k == 2:
+            mat = m
+            for q in qs:
+                bi = last.get(q)
+                if bi is not None and blocks[bi] is not None and blocks[bi][0] == [q]:
+                    mat = torch.matmul(mat, _lift_to_pair([q], blocks[bi][1], qs))
+                    blocks[bi] = None
+            blocks.append([qs, mat])
+        else:
+            blocks.append([qs, m])
+        for q in qs:
+            last[q] = len(blocks) - 1
+    return [(b[0], b[1]) for b in blocks if b is not None]
 
 
 # --------------------------------------------------------------------------- #
@@ -175,7 +271,7 @@ class CompiledCircuit:
     """
 
     def __init__(self, gates, num_qubits: int, dtype: torch.dtype, batch_shape=(),
-                 geometry: TileGeometry = None):
+                 geometry: TileGeometry = None, merge: bool = True):
         from . import states
         n = num_qubits
         self.n = n
@@ -183,6 +279,7 @@ class CompiledCircuit:
         self.batch_shape = tuple(batch_shape)
         self.batch = _engine._prod(self.batch_shape)
         self.gates = [([int(q) for q in qs], m) for qs, m in gates]
+        self.num_source_gates = len(self.gates)
         for qs, m in self.gates:
             k = states.count_qubits_gate_matrix(m)
             if len(qs) != k or len(set(qs)) != k or not set(qs).issubset(range(n)):
@@ -195,6 +292,9 @@ class CompiledCircuit:
                                    f"state batch dims {self.batch_shape}")
         if self.gates:
             L.require_cuda(*[m for _, m in self.gates])
+        if merge and os.environ.get("UA_MERGE_GATES", "1") != "0":
+            with torch.no_grad():
+                self.gates = merge_gates(self.gates)
         self.geo = geometry or default_geometry(n, dtype)
         self.gate_bits = [[n - 1 - q for q in qs] for qs, _ in self.gates]
         self.passes = plan_passes(self.gate_bits, self.geo) if self.gates else []
