@@ -62,6 +62,16 @@ def main():
         cc = circuit.CompiledCircuit(gl, n, cd, (), geometry=geo, merge=False)
         print("passes", cc.num_passes, "gates", cc.num_gates)
         fn = lambda: cc.run(a, in_place=True)   # noqa
+    elif sc.startswith("bench"):           # bench:<layers>  -- the bench.py circuit (C2 recipe)
+        sys.path.insert(0, ROOT)
+        from bench import random_circuit
+        layers = int(sc.split(":")[1])
+        gl = [(qs, torch.as_tensor(u.astype(npc)).to(dev)) for qs, u in random_circuit(n, layers, 202)]
+        cc = circuit.CompiledCircuit(gl, n, cd)
+        print("passes", cc.num_passes, "gates", cc.num_gates, "source gates", cc.num_source_gates)
+        a.zero_()
+        a[0] = 1
+        fn = lambda: cc.run(a, in_place=True)   # noqa
     elif sc == "phase":
         ang = torch.rand(2 ** n, dtype=torch.float32 if args.dtype == "c64" else torch.float64, device=dev)
         fn = lambda: ua.simulation.apply_phase(ang, a)   # noqa
