@@ -43,6 +43,27 @@ template <typename C> __device__ __forceinline__ C cmul(const C a, const C b) {
     return r;
 }
 
+// ------------------------------------------------------------------ packed fp32 (FFMA2)
+// Blackwell issues fma.rn.f32x2 (SASS FFMA2) at ~1.5x the scalar FFMA FLOP rate (measured
+// 69.7 vs 45.7 TFLOP/s, tools/micro/ffma_rate.cu).  A complex MAC acc += g*x is two FFMA2:
+//   acc = (g.re,g.re)*(x.re,x.im) + acc ;  acc = (-g.im,g.im)*(x.im,x.re) + acc
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(f32x2_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2_t ffma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // ------------------------------------------------------------------ index helpers
 // insert a zero bit at position p (bits >= p move up by one)
 __host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t x, int p) {

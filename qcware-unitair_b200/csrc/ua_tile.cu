@@ -54,6 +54,8 @@ struct FusedArgs {
     // dimension j spans element-index bits [tstart[j], tstart[j+1]); a tile is the box made
     // of the low bits of every dimension, moved by ONE cp.async.bulk.tensor instruction.
     int swizzle;                 // 1: bank-conflict-free member swizzle for low targets
+    int use_f2;                  // 1: complex64 gate phase with packed FFMA2
+    int l2_prefetch;             // 1: L2-prefetch the tile this CTA will load next
     int trank;                   // 0 = tensor path off (per-run bulk copies instead)
     int tstart[6];
     alignas(64) CUtensorMap tmap_in;
@@ -110,6 +112,16 @@ __device__ __forceinline__ void tma_load(int rank, unsigned dst, const CUtensorM
                              ::"r"(dst), "l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(bar) : "memory"); break;
     }
 }
+__device__ __forceinline__ void tma_prefetch_l2(int rank, const CUtensorMap *tm, const int *c) {
+    const unsigned long long t = reinterpret_cast<unsigned long long>(tm);
+    switch (rank) {
+        case 1: asm volatile("cp.async.bulk.prefetch.tensor.1d.L2.global.tile [%0, {%1}];" ::"l"(t), "r"(c[0]) : "memory"); break;
+        case 2: asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(t), "r"(c[0]), "r"(c[1]) : "memory"); break;
+        case 3: asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]) : "memory"); break;
+        case 4: asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]) : "memory"); break;
+        default: asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(t), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]) : "memory"); break;
+    }
+}
 __device__ __forceinline__ void tma_store(int rank, const CUtensorMap *tm, const int *c, unsigned src) {
     const unsigned long long t = reinterpret_cast<unsigned long long>(tm);
     switch (rank) {
@@ -128,6 +140,7 @@ __device__ __forceinline__ void tma_store(int rank, const CUtensorMap *tm, const
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 __device__ __forceinline__ unsigned insert_zero32(unsigned x, int p) {
     const unsigned lo = x & ((1u << p) - 1u);
@@ -280,36 +293,161 @@ __device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
     }
 }
 
-template <typename R, int K, bool LOW>
+// complex64 gate on the tile with packed FFMA2.  With P = sum (gr,gr)*(xr,xi) and
+// Q = sum (gi,gi)*(xr,xi) the product is (P.x - Q.y, P.y + Q.x): two FFMA2 per complex MAC, the
+// amplitude pair comes straight from the 16-byte load and the matrix scalar is broadcast by the
+// instruction itself, so there are no operand shuffles.
+__device__ __forceinline__ float2 combine_pq(f32x2_t P, f32x2_t Q) {
+    const float2 p = unpack2(P), q = unpack2(Q);
+    return make_float2(p.x - q.y, p.y + q.x);
+}
+
+// scatter the bits of x around the (ascending) zero-insertion points vb[]: a bit permutation,
+// so scatter(x | y) = scatter(x) | scatter(y) for disjoint x, y
+template <int KH>
+__device__ __forceinline__ unsigned scatter_bits(unsigned x, const int (&vb)[KH > 0 ? KH : 1]) {
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+        const unsigned himask = ~0u << vb[i];
+        x += x & himask;                 // bits >= vb[i] move up by one
+    }
+    return x;
+}
+
+// Fast path: the tile has at least NT*GU groups (true for the production tile sizes), so there is
+// no tail predicate, the thread part of every address is computed once per gate and the group
+// part is warp-uniform.
+template <int K, bool LOW, int NT>
+__device__ __forceinline__ void apply_gate_smem_f2(ulonglong2 *tv, const float2 *M,
+                                                   const FusedGate &gd, int TV) {
+    constexpr int KH = LOW ? K - 1 : K;
+    constexpr int NV = 1 << KH;
+    constexpr int D = 1 << K;
+    constexpr int GU = (NV >= 8) ? 1 : 8 / NV;       // 8 vectors (16 amplitudes) per thread in flight
+    int vb[KH > 0 ? KH : 1];
+    unsigned off[KH > 0 ? KH : 1];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+        vb[i] = (int)gd.sb[i + (LOW ? 1 : 0)] - 1;
+        off[i] = 1u << vb[i];
+    }
+    // the matrix stays unexpanded (re, im): FFMA2 takes a scalar register broadcast to both
+    // lanes (SASS "R.F32" operand), so pack2(g, g) costs nothing
+    constexpr bool MREG = (K <= 2);
+    float2 mr[MREG ? D * D : 1];
+    if (MREG) {
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) mr[e] = M[e];
+    }
+    auto Mat = [&](int s, int t) -> float2 { return MREG ? mr[s * D + t] : M[s * D + t]; };
+    const f32x2_t zero = pack2(0.f, 0.f);
+
+    const unsigned groups = 1u << (TV - KH);
+    const unsigned tbase = scatter_bits<KH>(threadIdx.x, vb);          // per thread, once per gate
+    for (unsigned g0 = 0; g0 < groups; g0 += NT * GU) {                 // warp-uniform
+        ulonglong2 *p[GU];
+        ulonglong2 x[GU][NV];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            p[u] = tv + (tbase | scatter_bits<KH>(g0 + u * NT, vb));
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                unsigned o = 0;
+#pragma unroll
+                for (int i = 0; i < KH; ++i)
+                    if ((c >> i) & 1) o |= off[i];
+                x[u][c] = p[u][o];
+            }
+        }
+#pragma unroll
+        for (int ov = 0; ov < NV; ++ov) {
+            f32x2_t Pa[GU], Qa[GU], Pb[GU], Qb[GU];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) { Pa[u] = zero; Qa[u] = zero; Pb[u] = zero; Qb[u] = zero; }
+            if constexpr (LOW) {
+                // rows 2ov, 2ov+1; member t is half (t & 1) of vector t >> 1
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    const float2 ga = Mat(2 * ov, t), gb = Mat(2 * ov + 1, t);
+                    const f32x2_t gar = pack2(ga.x, ga.x), gai = pack2(ga.y, ga.y);
+                    const f32x2_t gbr = pack2(gb.x, gb.x), gbi = pack2(gb.y, gb.y);
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) {
+                        const f32x2_t X = (t & 1) ? x[u][t >> 1].y : x[u][t >> 1].x;
+                        Pa[u] = ffma2(gar, X, Pa[u]);
+                        Qa[u] = ffma2(gai, X, Qa[u]);
+                        Pb[u] = ffma2(gbr, X, Pb[u]);
+                        Qb[u] = ffma2(gbi, X, Qb[u]);
+                    }
+                }
+            } else {
+                // row ov for both amplitudes of every vector
+#pragma unroll
+                for (int t = 0; t < D; ++t) {
+                    const float2 gm = Mat(ov, t);
+                    const f32x2_t gr = pack2(gm.x, gm.x), gi = pack2(gm.y, gm.y);
+#pragma unroll
+                    for (int u = 0; u < GU; ++u) {
+                        Pa[u] = ffma2(gr, x[u][t].x, Pa[u]);
+                        Qa[u] = ffma2(gi, x[u][t].x, Qa[u]);
+                        Pb[u] = ffma2(gr, x[u][t].y, Pb[u]);
+                        Qb[u] = ffma2(gi, x[u][t].y, Qb[u]);
+                    }
+                }
+            }
+            unsigned o = 0;
+#pragma unroll
+            for (int i = 0; i < KH; ++i)
+                if ((ov >> i) & 1) o |= off[i];
+#pragma unroll
+            for (int u = 0; u < GU; ++u) {
+                const float2 r0 = combine_pq(Pa[u], Qa[u]), r1 = combine_pq(Pb[u], Qb[u]);
+                reinterpret_cast<float4 *>(p[u])[o] = make_float4(r0.x, r0.y, r1.x, r1.y);
+            }
+        }
+    }
+}
+
+template <typename R, int K, bool LOW, int NT>
 __device__ __forceinline__ void apply_gate_swz(typename VecOf<R>::type *tv,
                                                const typename CplxOf<R>::type *M,
-                                               const FusedGate &gd, int TV, int nthreads, bool allow_swz) {
+                                               const FusedGate &gd, int TV, bool allow_swz, bool use_f2) {
+    constexpr int nthreads = NT;
     constexpr int APVLOG = VecOf<R>::APV == 2 ? 1 : 0;
     constexpr int KH = LOW ? K - 1 : K;
     bool swz = false;
     if constexpr (KH > 0) swz = allow_swz && ((int)gd.sb[LOW ? 1 : 0] - APVLOG) < 3;   // lowest vector-level target
+    if constexpr (sizeof(R) == 4) {      // complex64: packed FFMA2 fast path on full-size tiles
+        constexpr int NVf = 1 << KH;
+        constexpr int GUf = (NVf >= 8) ? 1 : 8 / NVf;
+        if (use_f2 && !swz && (1u << (TV - KH)) >= (unsigned)(NT * GUf)) {
+            apply_gate_smem_f2<K, LOW, NT>(reinterpret_cast<ulonglong2 *>(tv),
+                                           reinterpret_cast<const float2 *>(M), gd, TV);
+            return;
+        }
+    }
     if constexpr (KH > 0 && K <= 2) {   // 3-qubit gates (rare after merging) keep the plain path
         if (swz) { apply_gate_smem<R, K, LOW, true>(tv, M, gd, TV, nthreads); return; }
     }
     apply_gate_smem<R, K, LOW, false>(tv, M, gd, TV, nthreads);
 }
 
-template <typename R>
+template <typename R, int NT>
 __device__ __forceinline__ void apply_any_gate(typename VecOf<R>::type *tv,
                                                const typename CplxOf<R>::type *M,
-                                               const FusedGate &gd, int TV, int nthreads, bool swz) {
+                                               const FusedGate &gd, int TV, bool swz, bool f2) {
     constexpr int APV = VecOf<R>::APV;
     if constexpr (APV == 2) {
         if (gd.sb[0] == 0) {
-            if (gd.k == 1) apply_gate_swz<R, 1, true>(tv, M, gd, TV, nthreads, swz);
-            else if (gd.k == 2) apply_gate_swz<R, 2, true>(tv, M, gd, TV, nthreads, swz);
-            else apply_gate_swz<R, 3, true>(tv, M, gd, TV, nthreads, swz);
+            if (gd.k == 1) apply_gate_swz<R, 1, true, NT>(tv, M, gd, TV, swz, f2);
+            else if (gd.k == 2) apply_gate_swz<R, 2, true, NT>(tv, M, gd, TV, swz, f2);
+            else apply_gate_swz<R, 3, true, NT>(tv, M, gd, TV, swz, f2);
             return;
         }
     }
-    if (gd.k == 1) apply_gate_swz<R, 1, false>(tv, M, gd, TV, nthreads, swz);
-    else if (gd.k == 2) apply_gate_swz<R, 2, false>(tv, M, gd, TV, nthreads, swz);
-    else apply_gate_swz<R, 3, false>(tv, M, gd, TV, nthreads, swz);
+    if (gd.k == 1) apply_gate_swz<R, 1, false, NT>(tv, M, gd, TV, swz, f2);
+    else if (gd.k == 2) apply_gate_swz<R, 2, false, NT>(tv, M, gd, TV, swz, f2);
+    else apply_gate_swz<R, 3, false, NT>(tv, M, gd, TV, swz, f2);
 }
 
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  Shared memory layout:
@@ -413,9 +551,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 512 / FUSED_THREADS) fused_pass
     for (long long tile_id = first; tile_id < a.num_tiles; tile_id += step, ++it) {
         const int s = (int)(it % nstage);
         const unsigned parity = (unsigned)((it / nstage) & 1);
-        // prefetch tile it+nstage-1 into the stage that tile it-1 used (its store was issued
-        // at the end of the previous iteration: wait until the engine has read it)
-        if (mover) {
+        // nstage <= 2: prefetch tile it+nstage-1 into the stage that tile it-1 used (its store
+        // was issued at the end of the previous iteration: wait until the engine has read it).
+        // nstage >= 3 refills at the END of the iteration instead (below), when that store has
+        // had a whole gate phase to drain, so warp 0 never stalls on it.
+        if (mover && nstage <= 2) {
             const long long tn = tile_id + (long long)(nstage - 1) * step;
             if (tn < a.num_tiles) {
                 bulk_wait_read_all();
@@ -448,16 +588,37 @@ __global__ void __launch_bounds__(FUSED_THREADS, 512 / FUSED_THREADS) fused_pass
             __syncthreads();
         }
         mbar_wait(smem_u32(&bars[s]), parity);
+        // single-buffered CTAs cannot load ahead: at least pull the next tile into L2 now so the
+        // real load after this tile's store is an L2 hit
+        if (a.l2_prefetch && a.trank > 0 && threadIdx.x == 0) {
+            const long long tn = tile_id + (long long)nstage * step;
+            if (tn < a.num_tiles) {
+                long long row;
+                int c[5];
+                tensor_coords(tile_base(tn, row), c);
+                tma_prefetch_l2(a.trank, &a.tmap_in, c);
+            }
+        }
 
         V *tv = reinterpret_cast<V *>(smem_raw + (size_t)s * tile_bytes);
         for (int g = 0; g < a.num_gates; ++g) {
             const FusedGate &gd = a.gates[g];
-            apply_any_gate<R>(tv, sM + gd.smoff, gd, TV, FUSED_THREADS, a.swizzle != 0);
+            apply_any_gate<R, FUSED_THREADS>(tv, sM + gd.smoff, gd, TV, a.swizzle != 0, a.use_f2 != 0);
             if (g + 1 < a.num_gates) __syncthreads();
         }
         fence_proxy_async();        // make the generic-proxy writes visible to the copy engine
         __syncthreads();
-        if (mover) issue_store(tile_id, s);
+        if (mover) {
+            issue_store(tile_id, s);
+            if (nstage >= 3) {
+                const long long tn = tile_id + (long long)(nstage - 1) * step;
+                if (tn < a.num_tiles) {
+                    bulk_wait_read_but_one();      // store of tile it-1 has left shared memory
+                    __syncwarp();
+                    issue_load(tn, (int)((it + nstage - 1) % nstage));
+                }
+            }
+        }
     }
     if (mover) bulk_wait_all();
 }
@@ -544,8 +705,12 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // shared memory budget per CTA: 512/FUSED_THREADS CTAs share an SM
-    const int ctas = 512 / FUSED_THREADS;
+    // shared memory budget per CTA: up to 512/FUSED_THREADS CTAs share an SM (fewer when
+    // UA_FUSED_CTAS says so or the tiles are too large)
+    int ctas = 512 / FUSED_THREADS;
+    const int want_ctas = env_int("UA_FUSED_CTAS", 0);
+    if (want_ctas >= 1 && want_ctas < ctas) ctas = want_ctas;
+    while (ctas > 1 && (size_t)(224 * 1024) / ctas - 1024 < tile_bytes + mat_bytes) --ctas;
     const size_t budget = (size_t)(224 * 1024) / ctas - 1024;
     int nstage = (budget > mat_bytes) ? (int)((budget - mat_bytes) / tile_bytes) : 0;
     if (nstage > 3) nstage = 3;
@@ -554,6 +719,8 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
     if (want >= 1 && want <= nstage) nstage = want;
     a.nstage = nstage;
     a.swizzle = env_int("UA_FUSED_SWZ", 0);
+    a.use_f2 = env_int("UA_FUSED_F2", 0);
+    a.l2_prefetch = env_int("UA_FUSED_L2PF", nstage <= 2 ? 1 : 0);
     const size_t smem = (size_t)nstage * tile_bytes + mat_bytes;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, smem);
@@ -642,12 +809,14 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
     // 256-thread CTAs run two per SM (phases of the two interleave); fall back to one
     // 512-thread CTA when two tiles do not fit
-    int threads = env_int("UA_FUSED_THREADS", 256);
-    if (threads == 256 && 2 * (tile_bytes + mat_bytes) > (size_t)222 * 1024) threads = 512;
+    int threads = env_int("UA_FUSED_THREADS", 128);   // 3 x 128-thread CTAs per SM measured best (profiles/)
+    if (threads <= 256 && 2 * (tile_bytes + mat_bytes) > (size_t)222 * 1024) threads = 512;
     if (dtype == UA_C64) {
+        if (threads == 128) return launch_fused<float, 128>(a, tile_bytes, mat_bytes, st);
         if (threads == 256) return launch_fused<float, 256>(a, tile_bytes, mat_bytes, st);
         return launch_fused<float, 512>(a, tile_bytes, mat_bytes, st);
     }
+    if (threads == 128) return launch_fused<double, 128>(a, tile_bytes, mat_bytes, st);
     if (threads == 256) return launch_fused<double, 256>(a, tile_bytes, mat_bytes, st);
     return launch_fused<double, 512>(a, tile_bytes, mat_bytes, st);
 }
