@@ -119,10 +119,39 @@ __global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
         V prev;
         // K >= 4: keep the row loop rolled, the fully unrolled body (8192 FMAs for K = 5)
         // overflows the instruction cache (ncu: stall_no_instruction dominated)
-#pragma unroll(K >= 4 ? 1 : NV)
+#pragma unroll(K >= 4 ? ((K == 5 && sizeof(R) == 8) ? 1 : 2) : NV)
         for (int ov = 0; ov < NV; ++ov) {
             V res;
-            if constexpr (APV == 1) {
+            if constexpr (APV == 2 && K >= 3) {
+                // complex64, FMA-bound sizes: packed FFMA2 (P = sum gr*(xr,xi), Q = sum gi*(xr,xi),
+                // result (P.x - Q.y, P.y + Q.x)); the matrix scalar is broadcast by the instruction
+                f32x2_t Pa = pack2(0.f, 0.f), Qa = Pa, Pb = Pa, Qb = Pa;
+                if constexpr (LOW) {
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        const V xv = x[u][t >> 1];
+                        const f32x2_t X = (t & 1) ? pack2(xv.z, xv.w) : pack2(xv.x, xv.y);
+                        const C ga = Uat(2 * ov, t), gb = Uat(2 * ov + 1, t);
+                        Pa = ffma2(pack2(ga.x, ga.x), X, Pa);
+                        Qa = ffma2(pack2(ga.y, ga.y), X, Qa);
+                        Pb = ffma2(pack2(gb.x, gb.x), X, Pb);
+                        Qb = ffma2(pack2(gb.y, gb.y), X, Qb);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < D; ++t) {
+                        const C g = Uat(ov, t);
+                        const f32x2_t gr = pack2(g.x, g.x), gi = pack2(g.y, g.y);
+                        const f32x2_t X0 = pack2(x[u][t].x, x[u][t].y), X1 = pack2(x[u][t].z, x[u][t].w);
+                        Pa = ffma2(gr, X0, Pa);
+                        Qa = ffma2(gi, X0, Qa);
+                        Pb = ffma2(gr, X1, Pb);
+                        Qb = ffma2(gi, X1, Qb);
+                    }
+                }
+                const float2 pa = unpack2(Pa), qa = unpack2(Qa), pb = unpack2(Pb), qb = unpack2(Qb);
+                res = make_float4(pa.x - qa.y, pa.y + qa.x, pb.x - qb.y, pb.y + qb.x);
+            } else if constexpr (APV == 1) {
                 C acc = mk(R(0), R(0));
 #pragma unroll
                 for (int t = 0; t < D; ++t) cfma(acc, Uat(ov, t), x[u][t]);
