@@ -141,6 +141,12 @@ int ua_fused_limits(int dtype, int *max_tile_bits_out, int *max_matrix_elems_out
 int ua_permute_bits(int dtype, void *out, const void *in, int num_bits, long long batch,
                     const int *host_src_bit, void *stream);
 
+/* Sign-mask diagonal gates (CZ, CC...CZ and products), one pass, masks tested in-kernel:
+ * out[b, i] = in[b, i] * prod_m (-1)^[(i & mask_m) == mask_m]; mask bit p <-> index bit p.
+ * Replaces multi_cz / multi_controlled_z (operations.py:657-783).  out may alias in.         */
+int ua_apply_sign_masks(int dtype, void *out, const void *in, int num_qubits, long long batch,
+                        int num_masks, const unsigned long long *host_masks, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

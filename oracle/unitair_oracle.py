@@ -261,6 +261,51 @@ def swap(state, qubit_pair):
     return permute_qubits(perm, state)
 
 
+def multi_cz(qubit_pairs, state_vector):
+    """operations.py:657-748 -- sign vector prod_pairs (1 - 2*[(i & crit) == crit]) times the state."""
+    state_vector = np.asarray(state_vector)
+    n = count_qubits(state_vector)
+    pairs = np.asarray(qubit_pairs).reshape(-1, 2)
+    if (pairs >= n).any():
+        raise ValueError("Control/target indices for CZ gate must be less than num_bits.")
+    if (pairs[:, 0] == pairs[:, 1]).any():
+        raise ValueError("Control and target qubits are not distinct.")
+    idx = np.arange(2 ** n)
+    phases = np.ones(2 ** n, dtype=np.int64)
+    for c, t in pairs:
+        crit = 2 ** (n - c - 1) + 2 ** (n - t - 1)           # :729-731
+        phases *= 1 - 2 * ((idx & crit) == crit)              # :745-746
+    return (phases * state_vector).astype(state_vector.dtype)
+
+
+def multi_controlled_z(qubits, state_vector):
+    """operations.py:751-783 -- permute the listed qubits to the right, flip the sign of the
+    all-ones component of that subsystem, permute back."""
+    state_vector = np.asarray(state_vector)
+    n = count_qubits(state_vector)
+    qubits = list(qubits)
+    inert = [q for q in range(n) if q not in set(qubits)]
+    factors = np.ones(2 ** len(qubits))
+    factors[-1] = -1.0
+    factors = np.tile(factors, 2 ** len(inert))               # :770-772
+    perm = inert + qubits
+    reverse = [0] * n
+    for q, i in enumerate(perm):
+        reverse[i] = q
+    out = permute_qubits(perm, state_vector)
+    out = (factors * out).astype(state_vector.dtype)
+    return permute_qubits(reverse, out)
+
+
+def multi_controlled_x(state_vector, controls, target):
+    """operations.py:786-806 -- H on the target, C...CZ on controls + target, H on the target."""
+    state_vector = np.asarray(state_vector)
+    h = (np.array([[1, 1], [1, -1]]) * 2 ** -0.5).astype(state_vector.dtype)
+    out = apply_operator(h, [target], state_vector)
+    out = multi_controlled_z(list(controls) + [target], out)
+    return apply_operator(h, [target], out)
+
+
 # --------------------------------------------------------------------------- #
 # closed-form gradients (SURVEY.md section 3.4; PyTorch's conjugate-Wirtinger
 # convention).  The reference has no source for these (they come from torch's

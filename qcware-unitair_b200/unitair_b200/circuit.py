@@ -352,14 +352,59 @@ class CompiledCircuit:
         return out
 
 
+class _AdjointCircuit(torch.autograd.Function):
+    """Whole circuit as ONE autograd node with the adjoint method (unitary gates only).
+
+    forward: fused passes, nothing saved but the output state and the gate tensors.
+    backward: walk the gates in reverse; psi <- U^H psi recomputes the input of each gate,
+    grad_U = g psi^H (ua_gate_grad), g <- U^H g.  Memory: 2 states instead of one saved state
+    per parameterised gate (torch's tape through the reference needs 1.25 TiB for config C3,
+    SURVEY.md 7 hard part 4); cost: 3 passes per gate.
+    """
+
+    @staticmethod
+    def forward(ctx, state, n, qubit_lists, *mats):
+        gates = list(zip(qubit_lists, mats))
+        batch_shape = tuple(state.shape[:-1])
+        with torch.no_grad():
+            out = CompiledCircuit(gates, n, state.dtype, batch_shape).run(state)
+        ctx.n = n
+        ctx.qubit_lists = qubit_lists
+        ctx.save_for_backward(out, *mats)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        out, *mats = ctx.saved_tensors
+        n = ctx.n
+        dim = 1 << n
+        batch = out.numel() >> n
+        psi = out.clone()
+        g = _engine._aligned(grad_out).clone()
+        grads = [None] * len(mats)
+        for i in range(len(mats) - 1, -1, -1):
+            qs, m = ctx.qubit_lists[i], _engine._aligned(mats[i])
+            k = len(qs)
+            gstride = 0 if m.dim() == 2 else 4 ** k
+            _engine.launch_gate(psi, psi, m, n, k, qs, batch, dim, gstride, True)     # psi_in
+            if ctx.needs_input_grad[3 + i]:
+                grads[i] = _engine.launch_gate_grad(g, psi, n, k, qs, batch, dim, gstride, m.shape)
+            _engine.launch_gate(g, g, m, n, k, qs, batch, dim, gstride, True)         # grad wrt psi_in
+        grad_state = g if ctx.needs_input_grad[0] else None
+        return (grad_state, None, None, *grads)
+
+
 def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torch.Tensor,
-                in_place: bool = False) -> torch.Tensor:
+                in_place: bool = False, assume_unitary: bool = False) -> torch.Tensor:
     """Apply an ordered list of (qubits, operator) to a state in vector layout.
 
     Equivalent to calling simulation.apply_operator for each gate in turn.  Operators are
     (2^k, 2^k) or share the state's batch dims.  When no gradient is needed the list is
-    executed as fused shared-memory passes; with autograd (or broadcasting batch
-    structures) it runs one native gate kernel, and one autograd node, per gate.
+    executed as fused shared-memory passes.  With autograd it runs one native gate kernel and
+    one autograd node per gate (one saved state per gate that needs a gradient, like torch's
+    tape through the reference) -- unless assume_unitary=True, which differentiates the whole
+    list with the adjoint method: fused forward, no saved intermediate states.
     """
     from . import states
     from .simulation import operations as ops
@@ -369,7 +414,17 @@ def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torc
         state.requires_grad or any(m.requires_grad for _, m in gates))
     batch_shape = tuple(state.shape[:-1])
     simple = all(m.dim() == 2 or tuple(m.shape[:-2]) == batch_shape for _, m in gates)
-    if needs_grad or not simple or not state.is_complex() or any(m.dtype != state.dtype for _, m in gates):
+    uniform = simple and state.is_complex() and all(m.dtype == state.dtype for _, m in gates)
+    if needs_grad and assume_unitary and uniform and not in_place and gates and all(len(qs) <= L.MAX_GATE_QUBITS for qs, _ in gates):
+        L.require_cuda(state, *[m for _, m in gates])
+        for qs, m in gates:
+            k = states.count_qubits_gate_matrix(m)
+            if len(qs) != k or len(set(qs)) != k or not set(qs).issubset(range(n)):
+                raise ValueError(f"qubits={qs} is not a valid target list for a {k}-qubit operator "
+                                 f"on {n} qubits")
+        st = _engine._aligned(state)
+        return _AdjointCircuit.apply(st, n, [qs for qs, _ in gates], *[m for _, m in gates])
+    if needs_grad or not uniform:
         if in_place:
             raise RuntimeError("in_place=True is not available with autograd or broadcasting gates")
         out = state

@@ -212,3 +212,113 @@ def roll_qubits(state: torch.Tensor, num_steps=1):
     identity = list(range(num_qubits))
     perm = identity[-steps:] + identity[:-steps] if steps else identity
     return permute_qubits(perm, state)
+
+
+# --------------------------------------------------------------------------- #
+# sign-mask diagonal gates: SURVEY.md 8(f-3)
+# --------------------------------------------------------------------------- #
+class _SignMasks(torch.autograd.Function):
+    """out = D psi with D = diag(+-1) from bit masks; D is real and its own adjoint."""
+
+    @staticmethod
+    def forward(ctx, state, n, masks):
+        ctx.n, ctx.masks = n, masks
+        return _sign_masks_launch(state, n, masks)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad):
+        return _sign_masks_launch(_engine._aligned(grad), ctx.n, ctx.masks), None, None
+
+
+def _sign_masks_launch(state, n, masks):
+    import ctypes
+    dev = state.device
+    out = torch.empty_like(state)
+    batch = state.numel() >> n
+    if batch == 0:
+        return out
+    src = state
+    lib = _lib.lib()
+    with _lib.on_device(dev):
+        for i in range(0, max(len(masks), 1), 64):        # 64 masks per launch
+            chunk = masks[i:i + 64]
+            arr = (ctypes.c_ulonglong * max(len(chunk), 1))(*chunk)
+            _lib.check(lib.ua_apply_sign_masks(_lib.dtype_code(state.dtype), out.data_ptr(), src.data_ptr(),
+                                               n, batch, len(chunk), arr, _lib.stream_ptr(dev)))
+            src = out
+    return out
+
+
+def _apply_sign_masks(state_vector, num_qubits, masks):
+    _lib.require_cuda(state_vector)
+    was_real = not state_vector.is_complex()
+    st = state_vector
+    if was_real:
+        st = st.to(torch.complex128 if st.dtype == torch.float64 else torch.complex64)
+    st = _engine._aligned(st)
+    if torch.is_grad_enabled() and st.requires_grad:
+        out = _SignMasks.apply(st, num_qubits, list(masks))
+    else:
+        out = _sign_masks_launch(st, num_qubits, list(masks))
+    return out.real.contiguous() if was_real else out
+
+
+def multi_cz(qubit_pairs, state_vector: torch.Tensor, num_bits_memory_cutoff=None):
+    """Apply CZ gates to the given qubit pairs (operations.py:657-748).
+
+    `qubit_pairs` has size (2,) or (num_pairs, 2) (tensor or nested list).  The reference
+    builds a 2^n sign vector with arange/bitwise_and/prod (and needs a memory cutoff for it);
+    here the pair masks are tested inside one streaming kernel, so `num_bits_memory_cutoff`
+    is accepted and ignored.
+    """
+    num_qubits = states.count_qubits(state_vector)
+    if isinstance(qubit_pairs, torch.Tensor):
+        if qubit_pairs.dim() == 1:
+            qubit_pairs = qubit_pairs.view(1, 2)
+        elif qubit_pairs.dim() != 2:
+            raise ValueError('qubit_pairs must have size (2,) or (num_pairs, 2).')
+        pairs = qubit_pairs.tolist()
+    else:
+        pairs = list(qubit_pairs)
+        if pairs and not isinstance(pairs[0], (list, tuple)):
+            pairs = [pairs]
+    masks = []
+    for pair in pairs:
+        if len(pair) != 2:
+            raise ValueError('qubit_pairs must have size (2,) or (num_pairs, 2).')
+        c, t = int(pair[0]), int(pair[1])
+        if c >= num_qubits or t >= num_qubits or c < 0 or t < 0:
+            raise ValueError('Control/target indices for CZ gate must be less than num_bits.')
+        if c == t:
+            raise ValueError('Control and target qubits are not distinct.')
+        masks.append((1 << (num_qubits - 1 - c)) | (1 << (num_qubits - 1 - t)))
+    return _apply_sign_masks(state_vector, num_qubits, masks)
+
+
+def multi_controlled_z(qubits: Iterable[int], state_vector: torch.Tensor):
+    """Apply a CC...CZ gate to the given qubits (operations.py:751-783): the amplitude whose
+    listed bits are all 1 changes sign.  One pass instead of two full-state permutations."""
+    num_qubits = states.count_qubits(state_vector)
+    qubits = [int(q) for q in qubits]
+    if not set(qubits).issubset(range(num_qubits)):
+        raise ValueError(f'qubits={qubits} is not consistent with {num_qubits} qubits.')
+    mask = 0
+    for q in set(qubits):
+        mask |= 1 << (num_qubits - 1 - q)
+    if mask == 0:
+        return -state_vector if state_vector.numel() else state_vector.clone()
+    return _apply_sign_masks(state_vector, num_qubits, [mask])
+
+
+def multi_controlled_x(state_vector: torch.Tensor, controls: Iterable[int], target: int):
+    """C...CX as H . C...CZ . H on the target (operations.py:786-806)."""
+    controls = [int(c) for c in controls]
+    dtype = state_vector.dtype if state_vector.is_complex() else (
+        torch.complex128 if state_vector.dtype == torch.float64 else torch.complex64)
+    from .. import gates as _gates
+    h = _gates.hadamard(device=state_vector.device, dtype=dtype)
+    sv = state_vector if state_vector.is_complex() else state_vector.to(dtype)
+    sv = apply_operator(operator=h, qubits=[target], state=sv)
+    sv = multi_controlled_z(qubits=controls + [int(target)], state_vector=sv)
+    return apply_operator(operator=h, qubits=[target], state=sv)

@@ -314,17 +314,54 @@ def make_circuits(arrays, manifest):
     manifest["circuits"] = out_cases
 
 
+def make_diag(arrays, manifest):
+    """multi_cz / multi_controlled_z / multi_controlled_x / swap / permute."""
+    gen = torch.Generator().manual_seed(1007)
+    cases = []
+    specs = [("multi_cz", 4, (), [[0, 1]]), ("multi_cz", 6, (3,), [[0, 5], [2, 3], [5, 1]]),
+             ("multi_cz", 5, (), [3, 1]), ("multi_cz", 9, (2, 2), [[8, 0], [4, 7], [0, 4], [1, 2]]),
+             ("multi_controlled_z", 5, (), [0, 2, 4]), ("multi_controlled_z", 7, (3,), [6, 1]),
+             ("multi_controlled_z", 6, (), [5, 4, 3, 2, 1, 0]), ("multi_controlled_z", 3, (), [1]),
+             ("multi_controlled_x", 5, (), [[0, 3], 2]), ("multi_controlled_x", 6, (2,), [[5], 0]),
+             ("multi_controlled_x", 4, (), [[1, 2, 3], 0])]
+    for i, (fn, n, batch, arg) in enumerate(specs):
+        st = rnd_state(gen, n, batch, torch.complex64)
+        if fn == "multi_cz":
+            out = sim.multi_cz(torch.tensor(arg), st)
+        elif fn == "multi_controlled_z":
+            out = sim.multi_controlled_z(arg, st)
+        else:
+            out = sim.multi_controlled_x(st, controls=arg[0], target=arg[1])
+        key = f"dg{i}"
+        arrays[key + "_state"] = npy(st)
+        arrays[key + "_out"] = npy(out)
+        cases.append(dict(key=key, fn=fn, n=n, batch=list(batch), arg=arg, out_dtype=str(out.dtype)))
+    manifest["diag"] = cases
+
+
+ALL = [("apply_operator", make_apply_operator), ("apply_all", make_apply_all),
+       ("phase", make_phase), ("reductions", make_reductions),
+       ("grads", make_grads), ("circuits", make_circuits), ("diag", make_diag)]
+
+
 def main():
-    manifest = {"reference": "qcware/qcware-unitair v0.3.0 (/root/reference/src)",
-                "torch": torch.__version__}
-    for name, fn in [("apply_operator", make_apply_operator), ("apply_all", make_apply_all),
-                     ("phase", make_phase), ("reductions", make_reductions),
-                     ("grads", make_grads), ("circuits", make_circuits)]:
+    """make_golden.py [name ...]  -- regenerate all fixtures, or only the named ones."""
+    only = set(sys.argv[1:])
+    mpath = os.path.join(HERE, "manifest.json")
+    manifest = {}
+    if only and os.path.exists(mpath):
+        with open(mpath) as f:
+            manifest = json.load(f)
+    manifest["reference"] = "qcware/qcware-unitair v0.3.0 (/root/reference/src)"
+    manifest["torch"] = torch.__version__
+    for name, fn in ALL:
+        if only and name not in only:
+            continue
         arrays = {}
         fn(arrays, manifest)
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **arrays)
         print(name, len(arrays), "arrays")
-    with open(os.path.join(HERE, "manifest.json"), "w") as f:
+    with open(mpath, "w") as f:
         json.dump(manifest, f, indent=1)
 
 

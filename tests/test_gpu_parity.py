@@ -600,3 +600,85 @@ def test_full_size_properties_30_qubits(ua):
     z = torch.where((torch.arange(2 ** 10, device="cuda") & 1) == 0, 1.0, -1.0).repeat(2 ** (n - 10))
     ez = float(ua.diag_expectation_value(z, psi))
     assert abs(ez) < 1e-5
+
+
+# --------------------------------------------------------------------------- adjoint-method circuit autograd
+def test_adjoint_circuit_gradients(ua, golden):
+    """circuit.apply_gates(assume_unitary=True): one autograd node, no saved intermediate states.
+    Checked against the reference's torch-autograd gradient (golden C3) and against the
+    per-gate autograd path on a complex128 circuit."""
+    arr = golden.arrays("circuits")
+    m = golden.manifest["circuits"]["c3"]
+    n, layers = m["n"], m["layers"]
+    g = ua.gates
+    cn = g.cnot(device="cuda")
+    z0 = torch.where((torch.arange(2 ** n, device="cuda") >> (n - 1)) & 1 == 0, 1.0, -1.0)
+    for tag in ("c3", "c3b"):
+        theta = dev(arr[tag + "_theta"]).requires_grad_(True)
+        gates = []
+        for l in range(layers):
+            for q in range(n):
+                t = theta[l, q] if tag == "c3" else theta[:, l, q]
+                gates.append(([q], g.exp_y(t[..., 0])))
+                gates.append(([q], g.exp_z(t[..., 1])))
+            for q in range(n - 1):
+                gates.append(([q, q + 1], cn))
+        psi = ua.circuit.apply_gates(gates, dev(arr["c3_state"]), assume_unitary=True)
+        loss = ua.diag_expectation_value(z0, psi).sum()
+        g_theta, = torch.autograd.grad(loss, theta)
+        assert_close(host(psi), arr[tag + "_out"], "c64", factor=10, what=tag + " state")
+        assert_close(host(g_theta), arr[tag + "_gtheta"], "c64", factor=50, what=tag + " adjoint grad")
+    # complex128, state gradient too, vs the per-gate path
+    rng = np.random.default_rng(31)
+    n = 9
+    st0 = dev(rnd_state(rng, n, (3,), "c128"))
+    mats = [dev(haar(rng, 2 ** k, "c128")) for k in (1, 2, 1, 3, 2, 1, 2)]
+    qls = [[4], [1, 7], [0], [8, 2, 5], [3, 4], [8], [6, 0]]
+    w = dev(rnd_c(rng, (3, 2 ** n), "c128"))
+    res = []
+    for unitary in (True, False):
+        st = st0.clone().requires_grad_(True)
+        ms = [mm.clone().requires_grad_(True) for mm in mats]
+        out = ua.circuit.apply_gates(list(zip(qls, ms)), st, assume_unitary=unitary)
+        loss = (out * w.conj()).real.sum()
+        res.append(torch.autograd.grad(loss, [st] + ms))
+    for a, b in zip(*res):
+        assert_close(host(a), host(b), "c128", factor=50, what="adjoint vs per-gate")
+
+
+# --------------------------------------------------------------------------- sign-mask diagonal gates
+def test_multi_cz_family(ua, golden):
+    arr = golden.arrays("diag")
+    for c in golden.manifest["diag"]:
+        k = c["key"]
+        st = dev(arr[k + "_state"])
+        if c["fn"] == "multi_cz":
+            out = ua.simulation.multi_cz(torch.tensor(c["arg"], device="cuda"), st)
+        elif c["fn"] == "multi_controlled_z":
+            out = ua.simulation.multi_controlled_z(c["arg"], st)
+        else:
+            out = ua.simulation.multi_controlled_x(st, controls=c["arg"][0], target=c["arg"][1])
+        assert tuple(out.shape) == arr[k + "_out"].shape and str(out.dtype) == c["out_dtype"]
+        assert_close(host(out), arr[k + "_out"], "c64", what=str(c))
+    # equivalence with the dense CZ gate (the reference has no tests for these functions)
+    rng = np.random.default_rng(40)
+    for dt in ("c64", "c128"):
+        st = dev(rnd_state(rng, 11, (3,), dt))
+        a = ua.simulation.multi_cz([[2, 9], [0, 10]], st)
+        cz = ua.gates.cz(device="cuda", dtype=CD[dt])
+        b = ua.simulation.apply_operator(cz, (0, 10), ua.simulation.apply_operator(cz, (2, 9), st))
+        assert torch.equal(a, b)                       # sign flips are exact
+        ccz = ua.simulation.multi_controlled_z([1, 4, 7], st)
+        assert_close(host(ccz), orc.multi_controlled_z([1, 4, 7], host(st)), dt)
+    many = [[i, (i + 3) % 12] for i in range(12)] * 7        # > 64 masks -> several launches
+    st = dev(rnd_state(rng, 12, (), "c64"))
+    assert_close(host(ua.simulation.multi_cz(many, st)), orc.multi_cz(many, host(st)), "c64")
+    with pytest.raises(ValueError):
+        ua.simulation.multi_cz([[0, 12]], st)
+    with pytest.raises(ValueError):
+        ua.simulation.multi_cz([[3, 3]], st)
+    # gradient: D is its own adjoint
+    s2 = dev(rnd_state(rng, 6, (), "c128")).requires_grad_(True)
+    w = dev(rnd_c(rng, (64,), "c128"))
+    g, = torch.autograd.grad((ua.simulation.multi_cz([[0, 5]], s2) * w.conj()).real.sum(), s2)
+    assert_close(host(g), orc.multi_cz([[0, 5]], host(w)), "c128")

@@ -79,6 +79,21 @@ def test_circuit_c2_c4_golden(golden):
     assert_close(psi, arr["c4_out"], "c128", factor=10)
 
 
+def test_diag_golden(golden):
+    arr = golden.arrays("diag")
+    for c in golden.manifest["diag"]:
+        k = c["key"]
+        st = arr[k + "_state"]
+        if c["fn"] == "multi_cz":
+            out = orc.multi_cz(c["arg"], st)
+        elif c["fn"] == "multi_controlled_z":
+            out = orc.multi_controlled_z(c["arg"], st)
+        else:
+            out = orc.multi_controlled_x(st, c["arg"][0], c["arg"][1])
+        assert out.shape == arr[k + "_out"].shape
+        assert_close(out, arr[k + "_out"], "c64", what=str(c))
+
+
 def test_docs_known_answers():
     """Known-answer vectors in the reference docs."""
     q = np.array([[1, 5 - 1j], [5 + 1j, -1]], dtype=np.complex64)   # first_example.rst:74-75
