@@ -56,6 +56,8 @@ struct FusedArgs {
     int swizzle;                 // 1: bank-conflict-free member swizzle for low targets
     int use_f2;                  // 1: complex64 gate phase with packed FFMA2
     int l2_prefetch;             // 1: L2-prefetch the tile this CTA will load next
+    int stagger_ns;              // start delay per co-resident CTA index (breaks lockstep)
+    int num_sms;
     int trank;                   // 0 = tensor path off (per-run bulk copies instead)
     int tstart[6];
     alignas(64) CUtensorMap tmap_in;
@@ -157,7 +159,7 @@ template <typename V> __device__ __forceinline__ void cond_swap(V &a, V &b, bool
 // bit 0, i.e. inside the float4; SWZ: some vector-level target is among the 3 lowest vector
 // bits (bank-conflict avoiding member swizzle on).  `tv` is the tile as 16-byte vectors,
 // TV = log2 of their count.  GU groups are processed together for memory-level parallelism.
-template <typename R, int K, bool LOW, bool SWZ>
+template <typename R, int K, bool LOW, bool SWZ, bool LEAN = false>
 __device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
                                                 const typename CplxOf<R>::type *M,
                                                 const FusedGate &gd, int TV, int nthreads) {
@@ -169,7 +171,7 @@ __device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
     constexpr int NV = 1 << KH;
     constexpr int D = 1 << K;
     constexpr int INFLIGHT = sizeof(R) == 4 ? 4 : 2;  // 16-byte vectors in flight per thread
-    constexpr int GU = (K >= 2 || NV >= INFLIGHT) ? 1 : INFLIGHT / NV;   // K >= 2: the matrix fills the registers
+    constexpr int GU = (LEAN || K >= 2 || NV >= INFLIGHT) ? 1 : INFLIGHT / NV;   // K >= 2: the matrix fills the registers
 
     int vb[KH > 0 ? KH : 1];          // ascending vector-bit positions of the vector-level targets
     unsigned off[KH > 0 ? KH : 1];
@@ -189,7 +191,9 @@ __device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
             if (i < m) msk |= ((lane >> (3 - m + i)) & 1u) << i;
     }
 
-    constexpr bool MREG = (K <= 2);
+    // LEAN (3 CTAs x 256 threads per SM, <= 80 registers): complex128 2-qubit matrices stay in
+    // shared memory
+    constexpr bool MREG = LEAN ? (K <= (sizeof(R) == 4 ? 2 : 1)) : (K <= 2);
     C mr[MREG ? D * D : 1];
     if (MREG) {
 #pragma unroll
@@ -408,7 +412,7 @@ __device__ __forceinline__ void apply_gate_smem_f2(ulonglong2 *tv, const float2 
     }
 }
 
-template <typename R, int K, bool LOW, int NT>
+template <typename R, int K, bool LOW, int NT, bool LEAN>
 __device__ __forceinline__ void apply_gate_swz(typename VecOf<R>::type *tv,
                                                const typename CplxOf<R>::type *M,
                                                const FusedGate &gd, int TV, bool allow_swz, bool use_f2) {
@@ -417,6 +421,10 @@ __device__ __forceinline__ void apply_gate_swz(typename VecOf<R>::type *tv,
     constexpr int KH = LOW ? K - 1 : K;
     bool swz = false;
     if constexpr (KH > 0) swz = allow_swz && ((int)gd.sb[LOW ? 1 : 0] - APVLOG) < 3;   // lowest vector-level target
+    if constexpr (LEAN) {                 // register-lean build: plain scalar path only
+        apply_gate_smem<R, K, LOW, false, true>(tv, M, gd, TV, nthreads);
+        return;
+    }
     if constexpr (sizeof(R) == 4) {      // complex64: packed FFMA2 fast path on full-size tiles
         constexpr int NVf = 1 << KH;
         constexpr int GUf = (NVf >= 8) ? 1 : 8 / NVf;
@@ -432,28 +440,29 @@ __device__ __forceinline__ void apply_gate_swz(typename VecOf<R>::type *tv,
     apply_gate_smem<R, K, LOW, false>(tv, M, gd, TV, nthreads);
 }
 
-template <typename R, int NT>
+template <typename R, int NT, bool LEAN>
 __device__ __forceinline__ void apply_any_gate(typename VecOf<R>::type *tv,
                                                const typename CplxOf<R>::type *M,
                                                const FusedGate &gd, int TV, bool swz, bool f2) {
     constexpr int APV = VecOf<R>::APV;
     if constexpr (APV == 2) {
         if (gd.sb[0] == 0) {
-            if (gd.k == 1) apply_gate_swz<R, 1, true, NT>(tv, M, gd, TV, swz, f2);
-            else if (gd.k == 2) apply_gate_swz<R, 2, true, NT>(tv, M, gd, TV, swz, f2);
-            else apply_gate_swz<R, 3, true, NT>(tv, M, gd, TV, swz, f2);
+            if (gd.k == 1) apply_gate_swz<R, 1, true, NT, LEAN>(tv, M, gd, TV, swz, f2);
+            else if (gd.k == 2) apply_gate_swz<R, 2, true, NT, LEAN>(tv, M, gd, TV, swz, f2);
+            else apply_gate_swz<R, 3, true, NT, LEAN>(tv, M, gd, TV, swz, f2);
             return;
         }
     }
-    if (gd.k == 1) apply_gate_swz<R, 1, false, NT>(tv, M, gd, TV, swz, f2);
-    else if (gd.k == 2) apply_gate_swz<R, 2, false, NT>(tv, M, gd, TV, swz, f2);
-    else apply_gate_swz<R, 3, false, NT>(tv, M, gd, TV, swz, f2);
+    if (gd.k == 1) apply_gate_swz<R, 1, false, NT, LEAN>(tv, M, gd, TV, swz, f2);
+    else if (gd.k == 2) apply_gate_swz<R, 2, false, NT, LEAN>(tv, M, gd, TV, swz, f2);
+    else apply_gate_swz<R, 3, false, NT, LEAN>(tv, M, gd, TV, swz, f2);
 }
 
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  Shared memory layout:
 // [nstage tile buffers][gate matrices]; mbarriers are static.
-template <typename R, int FUSED_THREADS>
-__global__ void __launch_bounds__(FUSED_THREADS, 512 / FUSED_THREADS) fused_pass_kernel(const __grid_constant__ FusedArgs a) {
+template <typename R, int FUSED_THREADS, int MINB>
+__global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const __grid_constant__ FusedArgs a) {
+    constexpr bool LEAN = (FUSED_THREADS * MINB > 512);
     using C = typename CplxOf<R>::type;
     using V = typename VecOf<R>::type;
     constexpr int APVLOG = VecOf<R>::APV == 2 ? 1 : 0;
@@ -536,6 +545,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 512 / FUSED_THREADS) fused_pass
         bulk_commit();
     };
 
+    // co-resident CTAs start in lockstep (all load, then all compute) unless they are offset
+    if (a.stagger_ns > 0) {
+        const unsigned k = blockIdx.x / (unsigned)a.num_sms;
+        for (unsigned i = 0; i < k; ++i) __nanosleep((unsigned)a.stagger_ns);
+    }
     const long long first = blockIdx.x;
     const long long step = gridDim.x;
     // prologue: fill nstage-1 stages
@@ -603,7 +617,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 512 / FUSED_THREADS) fused_pass
         V *tv = reinterpret_cast<V *>(smem_raw + (size_t)s * tile_bytes);
         for (int g = 0; g < a.num_gates; ++g) {
             const FusedGate &gd = a.gates[g];
-            apply_any_gate<R, FUSED_THREADS>(tv, sM + gd.smoff, gd, TV, a.swizzle != 0, a.use_f2 != 0);
+            apply_any_gate<R, FUSED_THREADS, LEAN>(tv, sM + gd.smoff, gd, TV, a.swizzle != 0, a.use_f2 != 0);
             if (g + 1 < a.num_gates) __syncthreads();
         }
         fence_proxy_async();        // make the generic-proxy writes visible to the copy engine
@@ -693,10 +707,10 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <typename R, int FUSED_THREADS>
+template <typename R, int FUSED_THREADS, int MINB = 512 / FUSED_THREADS>
 static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = fused_pass_kernel<R, FUSED_THREADS>;
+    auto kern = fused_pass_kernel<R, FUSED_THREADS, MINB>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { set_error("ua_apply_fused_pass: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return UA_ERR_CUDA; }
@@ -707,7 +721,7 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // shared memory budget per CTA: up to 512/FUSED_THREADS CTAs share an SM (fewer when
     // UA_FUSED_CTAS says so or the tiles are too large)
-    int ctas = 512 / FUSED_THREADS;
+    int ctas = MINB;
     const int want_ctas = env_int("UA_FUSED_CTAS", 0);
     if (want_ctas >= 1 && want_ctas < ctas) ctas = want_ctas;
     while (ctas > 1 && (size_t)(224 * 1024) / ctas - 1024 < tile_bytes + mat_bytes) --ctas;
@@ -721,6 +735,8 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
     a.swizzle = env_int("UA_FUSED_SWZ", 0);
     a.use_f2 = env_int("UA_FUSED_F2", 0);
     a.l2_prefetch = env_int("UA_FUSED_L2PF", nstage <= 2 ? 1 : 0);
+    a.stagger_ns = env_int("UA_FUSED_STAGGER_NS", 0);
+    a.num_sms = sms;
     const size_t smem = (size_t)nstage * tile_bytes + mat_bytes;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, FUSED_THREADS, smem);
@@ -809,8 +825,14 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
     // 256-thread CTAs run two per SM (phases of the two interleave); fall back to one
     // 512-thread CTA when two tiles do not fit
-    int threads = env_int("UA_FUSED_THREADS", 128);   // 3 x 128-thread CTAs per SM measured best (profiles/)
-    if (threads <= 256 && 2 * (tile_bytes + mat_bytes) > (size_t)222 * 1024) threads = 512;
+    // measured best (profiles/): complex64 3 x 256-thread register-lean CTAs per SM ("768"),
+    // complex128 3 x 128-thread CTAs
+    int threads = env_int("UA_FUSED_THREADS", dtype == UA_C64 ? 768 : 128);
+    if (threads != 512 && 2 * (tile_bytes + mat_bytes) > (size_t)222 * 1024) threads = 512;
+    if (threads == 768) {     // 3 CTAs x 256 threads per SM, register-lean build
+        if (dtype == UA_C64) return launch_fused<float, 256, 3>(a, tile_bytes, mat_bytes, st);
+        return launch_fused<double, 256, 3>(a, tile_bytes, mat_bytes, st);
+    }
     if (dtype == UA_C64) {
         if (threads == 128) return launch_fused<float, 128>(a, tile_bytes, mat_bytes, st);
         if (threads == 256) return launch_fused<float, 256>(a, tile_bytes, mat_bytes, st);

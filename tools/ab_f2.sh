@@ -1,5 +1,10 @@
-for cfg in "128 12" "256 12" "128 11" "512 12"; do
-  set -- $cfg
-  echo "c128 threads=$1 tile=$2"
-  UA_FUSED_THREADS=$1 UA_TILE_BITS=$2 timeout 200 python tools/prof_one.py bench:6 --qubits 29 --dtype c128 --reps 2 | tail -2 | tr '\n' ' '; echo
+for th in 128 768; do
+  echo -n "threads=$th hi2q:9 "
+  UA_FUSED_THREADS=$th timeout 200 python tools/prof_one.py hi2q:9 --qubits 30 --reps 2 | tail -1
+  echo -n "threads=$th hi2q:1 "
+  UA_FUSED_THREADS=$th timeout 200 python tools/prof_one.py hi2q:1 --qubits 30 --reps 2 | tail -1
+  echo -n "threads=$th bench:6 "
+  UA_FUSED_THREADS=$th timeout 200 python tools/prof_one.py bench:6 --qubits 30 --reps 2 | tail -1
+  echo -n "threads=$th c128 bench:6 "
+  UA_FUSED_THREADS=$th timeout 200 python tools/prof_one.py bench:6 --qubits 29 --dtype c128 --reps 2 | tail -1
 done

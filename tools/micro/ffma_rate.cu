@@ -45,6 +45,34 @@ __global__ void k_ffma2(float *out, float a0, float b0, int iters) {
     for (int i = 0; i < CH; ++i) { float2 t = *reinterpret_cast<float2 *>(&acc[i]); s += t.x + t.y; }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// FFMA2 whose first operand is a scalar broadcast (pack2(g, g) -> SASS "R.F32" operand)
+template <int CH>
+__global__ void k_ffma2_bcast(float *out, float a0, float b0, int iters) {
+    unsigned long long acc[CH], b[CH];
+    float a[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        float2 t = make_float2(threadIdx.x * 0.001f + i, i * 0.5f);
+        acc[i] = *reinterpret_cast<unsigned long long *>(&t);
+        a[i] = a0 + i * 0.01f;
+        float2 tb = make_float2(b0 + i * 0.02f, b0 - i * 0.02f);
+        b[i] = *reinterpret_cast<unsigned long long *>(&tb);
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                unsigned long long aa;
+                asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a[(i + r) % CH]));
+                acc[i] = ffma2(aa, b[i], acc[i]);
+            }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { float2 t = *reinterpret_cast<float2 *>(&acc[i]); s += t.x + t.y; }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 template <typename F> float timeit(F f) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     f(); cudaDeviceSynchronize();
@@ -61,5 +89,7 @@ int main() {
     double fma2 = fma1 * 2;
     printf("FFMA : %.3f ms  %.2f TFLOP/s\n", ms1, 2 * fma1 / ms1 / 1e9);
     printf("FFMA2: %.3f ms  %.2f TFLOP/s\n", ms2, 2 * fma2 / ms2 / 1e9);
+    float ms3 = timeit([&] { k_ffma2_bcast<CH><<<blocks, threads>>>(out, 1.0001f, 0.9999f, iters); });
+    printf("FFMA2 (scalar-broadcast operand): %.3f ms  %.2f TFLOP/s\n", ms3, 2 * fma2 / ms3 / 1e9);
     return 0;
 }

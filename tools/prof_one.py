@@ -62,6 +62,19 @@ def main():
         cc = circuit.CompiledCircuit(gl, n, cd, (), geometry=geo, merge=False)
         print("passes", cc.num_passes, "gates", cc.num_gates)
         fn = lambda: cc.run(a, in_place=True)   # noqa
+    elif sc.startswith("hi2q"):            # hi2q:<count>  2-qubit gates on the tile's HIGH bits only
+        cnt = int(sc.split(":")[1])
+        geo = circuit.TileGeometry(n, args.tile, args.low, args.tile - args.low)
+        hb = list(range(n - (args.tile - args.low), n))          # bit positions
+        gl = []
+        for i in range(cnt):
+            b0, b1 = hb[i % len(hb)], hb[(i * 2 + 1) % len(hb)]
+            if b0 == b1:
+                b1 = hb[(i * 2 + 2) % len(hb)]
+            gl.append(([n - 1 - b0, n - 1 - b1], gate(2)))
+        cc = circuit.CompiledCircuit(gl, n, cd, (), geometry=geo, merge=False)
+        print("passes", cc.num_passes, "gates", cc.num_gates)
+        fn = lambda: cc.run(a, in_place=True)   # noqa
     elif sc.startswith("bench"):           # bench:<layers>  -- the bench.py circuit (C2 recipe)
         sys.path.insert(0, ROOT)
         from bench import random_circuit
