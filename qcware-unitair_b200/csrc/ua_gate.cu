@@ -191,6 +191,104 @@ __global__ void __launch_bounds__(256) gate_direct_kernel(const GateArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// complex128, k = 4 / 5: FP64 tensor cores (DMMA, mma.sync m8n8k4).  A dense 5-qubit block is a
+// genuine GEMM, Y(64 x N) = W(64 x 64) X(64 x N) in real arithmetic (W = [[Ur,-Ui],[Ui,Ur]]
+// interleaved), and on B200 the DFMA version is bound by the shared-memory broadcast of the
+// matrix (1 LDS.128 per 4 DFMA) at 18 TFLOP/s; DMMA needs one 8-byte fragment load per 256 MACs
+// and peaks at 37 TFLOP/s (tools/micro/dfma_rate.cu).  One warp owns 8 groups ("columns") at a
+// time: B fragments come straight from global memory (lane 4n+r holds real row 4j+r of group n),
+// A fragments stream from shared memory in fragment order, D fragments are paired across lanes
+// (shfl.xor 4) into 16-byte amplitudes and streamed out.
+struct DmmaArgs {
+    const void *in;
+    void *out;
+    const void *gate;
+    long long num_batches;         // batches of 8 groups
+    int spos[UA_MAX_GATE_QUBITS];  // ascending target bit positions (amplitude index)
+    int gbit[UA_MAX_GATE_QUBITS];
+    int adjoint;
+};
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) gate_dmma_kernel(const DmmaArgs a) {
+    constexpr int D = 1 << K;        // complex dimension
+    constexpr int MT = 2 * D / 8;    // 8-row tiles of the real matrix
+    constexpr int KS = 2 * D / 4;    // k-steps of 4 real rows
+    __shared__ double sW[MT * KS * 32];   // A fragments, fragment order
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // ---- matrix -> real fragments ------------------------------------------------------
+    {
+        const double2 *__restrict__ G = reinterpret_cast<const double2 *>(a.gate);
+        for (int e = threadIdx.x; e < MT * KS * 32; e += 256) {
+            const int l = e & 31, j = (e >> 5) % KS, i = (e >> 5) / KS;
+            const int row = 8 * i + (l >> 2), col = 4 * j + (l & 3);
+            const int s = row >> 1, cr = row & 1, t = col >> 1, cc = col & 1;
+            int gi = 0, gj = 0;
+#pragma unroll
+            for (int b = 0; b < K; ++b) {
+                gi |= ((s >> b) & 1) << a.gbit[b];
+                gj |= ((t >> b) & 1) << a.gbit[b];
+            }
+            double2 u;
+            if (a.adjoint) { u = G[gj * D + gi]; u.y = -u.y; }
+            else u = G[gi * D + gj];
+            sW[e] = (cr == cc) ? u.x : (cr == 0 ? -u.y : u.y);
+        }
+    }
+    __syncthreads();
+
+    uint64_t off[K];
+#pragma unroll
+    for (int b = 0; b < K; ++b) off[b] = 1ull << a.spos[b];
+    const double *__restrict__ in = reinterpret_cast<const double *>(a.in);
+    double2 *out = reinterpret_cast<double2 *>(a.out);
+    const int n_load = lane >> 2, r = lane & 3;             // B fragment: group n_load, real row 4j + r
+    const int comp = (lane >> 2) & 1;                        // D fragment: real row parity
+    const int n_store = 2 * (lane & 3) + comp;               // group this lane stores after pairing
+    const long long warps_total = (long long)gridDim.x * 8;
+    for (long long bt = (long long)blockIdx.x * 8 + warp; bt < a.num_batches; bt += warps_total) {
+        uint64_t base_l = (uint64_t)(bt * 8 + n_load), base_s = (uint64_t)(bt * 8 + n_store);
+#pragma unroll
+        for (int b = 0; b < K; ++b) { base_l = insert_zero(base_l, a.spos[b]); base_s = insert_zero(base_s, a.spos[b]); }
+        // ---- B fragments: this lane's component (r & 1) of amplitudes 2j + (r >> 1) ------------
+        double xb[KS];
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+            const int t = 2 * j + (r >> 1);
+            uint64_t idx = base_l;
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+                if ((t >> b) & 1) idx |= off[b];
+            xb[j] = __ldcs(in + 2 * idx + (r & 1));
+        }
+        // ---- 8 row tiles x KS k-steps ------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < KS; ++j) dmma_m8n8k4(d0, d1, sW[(i * KS + j) * 32 + lane], xb[j]);
+            // lane holds real row 8i + (lane>>2) of groups 2(lane&3), 2(lane&3)+1; the lane 4 above
+            // or below holds the other component of the same amplitude
+            const double send = comp ? d0 : d1;
+            const double recv = __shfl_xor_sync(0xffffffffu, send, 4);
+            const double2 amp = comp ? make_double2(recv, d1) : make_double2(d0, recv);
+            const int s = 4 * i + (lane >> 3);
+            uint64_t idx = base_s;
+#pragma unroll
+            for (int b = 0; b < K; ++b)
+                if ((s >> b) & 1) idx |= off[b];
+            __stcs(out + idx, amp);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Generic out-of-place kernel for 5 < k <= 10: one thread per output amplitude.  Slow
 // (re-reads through L1/L2) but complete; the reference accepts any k.
 struct GenericArgs {
@@ -331,11 +429,31 @@ extern "C" int ua_apply_gate(int dtype, void *out, const void *in, const void *g
         return check_launch("gate_generic_kernel");
     }
 
+    // (the DMMA path below needs the sorted targets; it is dispatched after the sort)
     // sort targets by bit position (ascending), remember their gate-index bit
     int order[UA_MAX_GATE_QUBITS];
     for (int j = 0; j < k; ++j) order[j] = j;
     for (int i = 1; i < k; ++i)
         for (int j = i; j > 0 && pos[order[j]] < pos[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
+
+    // complex128 dense 4-/5-qubit blocks with a shared gate: FP64 tensor cores
+    {
+        static int use_dmma = -1;
+        if (use_dmma < 0) { const char *e = getenv("UA_DMMA"); use_dmma = e ? atoi(e) : 1; }
+        const bool flat_c128 = dtype == UA_C128 && gate_batch_stride == 0 && (in_batch_stride == dim || batch == 1);
+        if (use_dmma && flat_c128 && (k == 4 || k == 5) && n - k >= 3) {
+            DmmaArgs d{};
+            d.in = in; d.out = out; d.gate = gate; d.adjoint = adjoint ? 1 : 0;
+            for (int i = 0; i < k; ++i) { d.spos[i] = pos[order[i]]; d.gbit[i] = k - 1 - order[i]; }
+            d.num_batches = (batch * (dim >> k)) / 8;
+            long long blocks = (d.num_batches + 7) / 8;
+            const long long cap = 148ll * 8;
+            if (blocks > cap) blocks = cap;
+            if (k == 4) gate_dmma_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(d);
+            else gate_dmma_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(d);
+            return check_launch("gate_dmma_kernel");
+        }
+    }
 
     GateArgs a;
     a.in = in; a.out = out; a.gate = gate; a.adjoint = adjoint ? 1 : 0;
