@@ -322,17 +322,35 @@ class ShardedCircuit:
                 w.wait()
         st.local, st.spare = dst, src
 
-    def run(self, st: ShardedState) -> ShardedState:
+    def run(self, st: ShardedState, timing: Optional[dict] = None) -> ShardedState:
+        """Execute the plan.  With `timing` (a dict) and a CUDA shard, per-phase device times
+        (ms, summed over epochs) are accumulated into it: permute / exchange / gates."""
         if st.layout != self.start_layout:
             raise RuntimeError("state layout does not match the layout this circuit was planned for")
         if st.world != self.world or st.n != self.n:
             raise RuntimeError("state does not match the circuit's size / world")
+        marks = []
+
+        def mark(tag):
+            if timing is not None and st.local.is_cuda:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((tag, ev))
+
+        mark("start")
         for ep, comp in zip(self.epochs, self.compiled):
             if ep.perm_src is not None:
                 out = self.engine.permute(ep.perm_src, st.local, st._spare())
                 st.local, st.spare = out, st.local
+                mark("permute")
             if ep.incoming:
                 self._exchange(st, ep)
+                mark("exchange")
             self.engine.run(comp, st.local)
+            mark("gates")
         st.layout = list(self.end_layout)
+        if marks:
+            torch.cuda.synchronize()
+            for (_, e0), (tag, e1) in zip(marks[:-1], marks[1:]):
+                timing[tag] = timing.get(tag, 0.0) + e0.elapsed_time(e1)
         return st
