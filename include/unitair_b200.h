@@ -136,6 +136,21 @@ int ua_apply_fused_pass(int dtype, void *out, const void *in, long long total_am
  * complex matrix elements (sum of 4^k over the gates) one pass can hold */
 int ua_fused_limits(int dtype, int *max_tile_bits_out, int *max_matrix_elems_out);
 
+/* Fused BACKWARD pass of the adjoint method for a pass of 1-/2-qubit UNITARY gates (same tile
+ * description as ua_apply_fused_pass, gates in FORWARD order).  In place on both buffers:
+ *   psi  : state AFTER the pass on entry, state BEFORE the pass on return (U^H applied in reverse)
+ *   grad : gradient w.r.t. the pass output on entry, w.r.t. its input on return
+ * For every gate g with host_gate_needs_grad[g] != 0, sum_r grad_out[a,r] conj(psi_in[b,r]) is
+ * ADDED to grad_acc (fp64 complex, zero-initialised by the caller, [rows or 1][sum 4^k] laid
+ * out like the forward pass's shared-memory matrices: gate g at element offset sum_{g'<g} 4^k',
+ * entry (s,t) in TARGET-BIT order: bit i of s <-> i-th lowest target bit position).            */
+int ua_fused_backward_pass(int dtype, void *psi, void *grad, long long total_amps,
+                           int total_bits, int tile_low_bits, int num_high,
+                           const int *host_high_pos, int num_gates, const int *host_gate_k,
+                           const int *host_gate_bits, const long long *host_gate_offset,
+                           const void *gate_mats, long long gate_row_stride,
+                           const int *host_gate_needs_grad, void *grad_acc, void *stream);
+
 /* Bit-permutation of the index (qubit swap / permute, operations.py:506-654), one pass:
  * out[b, i] = in[b, j] where bit host_src_bit[p] of j = bit p of i.                   */
 int ua_permute_bits(int dtype, void *out, const void *in, int num_bits, long long batch,

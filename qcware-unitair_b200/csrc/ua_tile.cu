@@ -637,6 +637,310 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
     if (mover) bulk_wait_all();
 }
 
+// =======================================================================================
+// Fused BACKWARD pass (adjoint method): psi and grad tiles are staged together; walking the
+// pass's gates in reverse, every gate does
+//     psi <- U^H psi            (recomputes the gate's input; gates are unitary)
+//     grad_U += g psi_in^H      (if the gate needs a gradient; summed in registers over the
+//                                thread's groups, over the warp by shuffles, over the CTA in
+//                                fp64 shared-memory accumulators)
+//     g   <- U^H g
+// and both tiles go back.  One read + one write of psi and of g (32 B / 64 B per amplitude)
+// for the whole pass instead of three passes per gate.  Gates are 1- or 2-qubit.
+struct BwdArgs {
+    FusedArgs f;                               // f.in = psi (in-out), f.out = grad (in-out)
+    double2 *acc;                              // [rows or 1][mat_elems] fp64 gradient accumulators
+    int mat_elems;
+    unsigned long long needs_grad;             // bit g: gate g needs a gradient
+};
+
+template <typename R, int K, bool LOW>
+__device__ __forceinline__ void bwd_gate_smem(typename VecOf<R>::type *tpsi, typename VecOf<R>::type *tg,
+                                              const typename CplxOf<R>::type *M /* U^H, register order */,
+                                              const FusedGate &gd, int TV, int nthreads, bool needs_grad,
+                                              double2 *sAcc /* this gate's D*D accumulators, register order */) {
+    using C = typename CplxOf<R>::type;
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    constexpr int APVLOG = APV == 2 ? 1 : 0;
+    constexpr int KH = LOW ? K - 1 : K;
+    constexpr int NV = 1 << KH;
+    constexpr int D = 1 << K;
+    constexpr int NG = (APV == 2 && !LOW) ? 2 : 1;     // independent groups per item
+    int vb[KH > 0 ? KH : 1];
+    unsigned off[KH > 0 ? KH : 1];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) {
+        vb[i] = (int)gd.sb[i + (LOW ? 1 : 0)] - APVLOG;
+        off[i] = 1u << vb[i];
+    }
+    C mr[D * D];
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) mr[e] = M[e];
+    R accx[D * D], accy[D * D];                    // grad[a][b] partial sums (register order)
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) { accx[e] = R(0); accy[e] = R(0); }
+
+    const unsigned groups = 1u << (TV - KH);
+    for (unsigned g = threadIdx.x; g < groups; g += nthreads) {
+        unsigned b = g;
+#pragma unroll
+        for (int i = 0; i < KH; ++i) b = insert_zero32(b, vb[i]);
+        V xv[NV], yv[NV];
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            unsigned idx = b;
+#pragma unroll
+            for (int i = 0; i < KH; ++i)
+                if ((c >> i) & 1) idx |= off[i];
+            xv[c] = tpsi[idx];
+            yv[c] = tg[idx];
+        }
+        V xo[NV], yo[NV];
+#pragma unroll
+        for (int h = 0; h < NG; ++h) {
+            // gather the 2^K amplitudes of this group
+            C x[D], y[D];
+#pragma unroll
+            for (int t = 0; t < D; ++t) {
+                if constexpr (APV == 1) { x[t] = xv[t]; y[t] = yv[t]; }
+                else if constexpr (LOW) {
+                    const V a = xv[t >> 1], bb = yv[t >> 1];
+                    x[t] = (t & 1) ? mk(a.z, a.w) : mk(a.x, a.y);
+                    y[t] = (t & 1) ? mk(bb.z, bb.w) : mk(bb.x, bb.y);
+                } else {
+                    x[t] = h ? mk(xv[t].z, xv[t].w) : mk(xv[t].x, xv[t].y);
+                    y[t] = h ? mk(yv[t].z, yv[t].w) : mk(yv[t].x, yv[t].y);
+                }
+            }
+            C xin[D], yin[D];
+#pragma unroll
+            for (int s = 0; s < D; ++s) {
+                C ax = mk(R(0), R(0)), ay = mk(R(0), R(0));
+#pragma unroll
+                for (int t = 0; t < D; ++t) { cfma(ax, mr[s * D + t], x[t]); cfma(ay, mr[s * D + t], y[t]); }
+                xin[s] = ax; yin[s] = ay;
+            }
+            if (needs_grad) {
+#pragma unroll
+                for (int aa = 0; aa < D; ++aa)
+#pragma unroll
+                    for (int bb = 0; bb < D; ++bb) {
+                        // y[aa] * conj(xin[bb])
+                        accx[aa * D + bb] = fma(y[aa].x, xin[bb].x, accx[aa * D + bb]);
+                        accx[aa * D + bb] = fma(y[aa].y, xin[bb].y, accx[aa * D + bb]);
+                        accy[aa * D + bb] = fma(y[aa].y, xin[bb].x, accy[aa * D + bb]);
+                        accy[aa * D + bb] = fma(-y[aa].x, xin[bb].y, accy[aa * D + bb]);
+                    }
+            }
+            // scatter back into vectors
+#pragma unroll
+            for (int t = 0; t < D; ++t) {
+                if constexpr (APV == 1) { xo[t] = xin[t]; yo[t] = yin[t]; }
+                else if constexpr (LOW) {
+                    if (t & 1) { xo[t >> 1].z = xin[t].x; xo[t >> 1].w = xin[t].y; yo[t >> 1].z = yin[t].x; yo[t >> 1].w = yin[t].y; }
+                    else { xo[t >> 1].x = xin[t].x; xo[t >> 1].y = xin[t].y; yo[t >> 1].x = yin[t].x; yo[t >> 1].y = yin[t].y; }
+                } else {
+                    if (h) { xo[t].z = xin[t].x; xo[t].w = xin[t].y; yo[t].z = yin[t].x; yo[t].w = yin[t].y; }
+                    else { xo[t].x = xin[t].x; xo[t].y = xin[t].y; yo[t].x = yin[t].x; yo[t].y = yin[t].y; }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < NV; ++c) {
+            unsigned idx = b;
+#pragma unroll
+            for (int i = 0; i < KH; ++i)
+                if ((c >> i) & 1) idx |= off[i];
+            tpsi[idx] = xo[c];
+            tg[idx] = yo[c];
+        }
+    }
+    if (needs_grad) {
+        // warp reduce, then one fp64 shared-memory atomic per entry per warp
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) {
+            R vx = accx[e], vy = accy[e];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vx += __shfl_xor_sync(0xffffffffu, vx, o);
+                vy += __shfl_xor_sync(0xffffffffu, vy, o);
+            }
+            if ((threadIdx.x & 31) == 0) {
+                atomicAdd(&sAcc[e].x, (double)vx);
+                atomicAdd(&sAcc[e].y, (double)vy);
+            }
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256, sizeof(R) == 4 ? 2 : 1) fused_bwd_kernel(const __grid_constant__ BwdArgs ba) {
+    using C = typename CplxOf<R>::type;
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    constexpr int APVLOG = APV == 2 ? 1 : 0;
+    constexpr int NT = 256;
+    const FusedArgs &a = ba.f;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bar;
+    const unsigned tile_bytes = (1u << a.T) * (unsigned)sizeof(C);
+    unsigned char *buf_psi = smem_raw, *buf_g = smem_raw + tile_bytes;
+    C *sM = reinterpret_cast<C *>(smem_raw + 2 * (size_t)tile_bytes);
+    double2 *sAcc = reinterpret_cast<double2 *>(smem_raw + 2 * (size_t)tile_bytes +
+                                                (((size_t)ba.mat_elems * sizeof(C) + 127) & ~(size_t)127));
+    const int TV = a.T - APVLOG;
+    const unsigned run_bytes = (1u << a.L) * (unsigned)sizeof(C);
+    const unsigned runs = 1u << a.H;
+    const unsigned lane = threadIdx.x & 31u;
+    const bool mover = threadIdx.x < 32;
+    constexpr int EBITS = sizeof(C) == 8 ? 0 : 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    for (int e = threadIdx.x; e < ba.mat_elems; e += NT) sAcc[e] = make_double2(0.0, 0.0);
+    __syncthreads();
+
+    auto tile_base = [&](long long tile_id, long long &row) -> uint64_t {
+        row = tile_id / a.tiles_per_row;
+        const long long j = tile_id - row * a.tiles_per_row;
+        uint64_t base = (uint64_t)j << a.L;
+        for (int i = 0; i < a.H; ++i) base = insert_zero(base, a.high[i]);
+        return base + ((uint64_t)row << a.total_bits);
+    };
+    auto run_offset = [&](unsigned r) -> uint64_t {
+        uint64_t o = 0;
+        for (int i = 0; i < a.H; ++i)
+            if ((r >> i) & 1u) o |= 1ull << a.high[i];
+        return o;
+    };
+    auto tensor_coords = [&](uint64_t base, int *c) {
+        const uint64_t e = base << EBITS;
+        for (int j = 0; j < a.trank; ++j) {
+            uint64_t v = e >> a.tstart[j];
+            if (j + 1 < a.trank) v &= (1ull << (a.tstart[j + 1] - a.tstart[j])) - 1ull;
+            c[j] = (int)v;
+        }
+    };
+    char *gp_psi = reinterpret_cast<char *>(const_cast<void *>(a.in));
+    char *gp_g = reinterpret_cast<char *>(a.out);
+
+    unsigned phase = 0;
+    long long last_row = -1;
+    for (long long tile_id = blockIdx.x; tile_id < a.num_tiles; tile_id += gridDim.x) {
+        long long row;
+        const uint64_t base = tile_base(tile_id, row);
+        // ---- load both tiles (previous stores must have left shared memory) ---------------
+        if (mover) {
+            bulk_wait_read_all();
+            __syncwarp();
+            const unsigned b32 = smem_u32(&bar);
+            if (lane == 0) mbar_arrive_expect_tx(b32, 2 * tile_bytes);
+            __syncwarp();
+            if (a.trank > 0) {
+                if (lane == 0) {
+                    int c[5];
+                    tensor_coords(base, c);
+                    tma_load(a.trank, smem_u32(buf_psi), &a.tmap_in, c, b32);
+                    tma_load(a.trank, smem_u32(buf_g), &a.tmap_out, c, b32);
+                }
+            } else {
+                for (unsigned r = lane; r < runs; r += 32) {
+                    const uint64_t o = (base + run_offset(r)) * sizeof(C);
+                    bulk_g2s(smem_u32(buf_psi) + r * run_bytes, gp_psi + o, run_bytes, b32);
+                    bulk_g2s(smem_u32(buf_g) + r * run_bytes, gp_g + o, run_bytes, b32);
+                }
+            }
+        }
+        // ---- adjoint matrices -> shared memory (register order); per-row gates reload per row
+        if (last_row < 0 || (a.mats_row_stride != 0 && row != last_row)) {
+            if (last_row >= 0 && a.mats_row_stride != 0) {
+                // flush the finished row's gradient accumulators
+                __syncthreads();
+                for (int e = threadIdx.x; e < ba.mat_elems; e += NT) {
+                    const double2 v = sAcc[e];
+                    atomicAdd(&ba.acc[last_row * ba.mat_elems + e].x, v.x);
+                    atomicAdd(&ba.acc[last_row * ba.mat_elems + e].y, v.y);
+                    sAcc[e] = make_double2(0.0, 0.0);
+                }
+            }
+            const C *__restrict__ mats = reinterpret_cast<const C *>(a.mats) + row * a.mats_row_stride;
+            for (int g = 0; g < a.num_gates; ++g) {
+                const FusedGate &gd = a.gates[g];
+                const int K = gd.k, D = 1 << K;
+                for (int e = threadIdx.x; e < D * D; e += NT) {
+                    const int sr = e >> K, t = e & (D - 1);
+                    int gi = 0, gj = 0;
+                    for (int i = 0; i < K; ++i) {
+                        gi |= ((sr >> i) & 1) << gd.gb[i];
+                        gj |= ((t >> i) & 1) << gd.gb[i];
+                    }
+                    sM[gd.smoff + e] = cconj(mats[gd.goff + gj * D + gi]);     // U^H
+                }
+            }
+            last_row = row;
+            __syncthreads();
+        }
+        mbar_wait(smem_u32(&bar), phase);
+        phase ^= 1u;
+
+        V *tpsi = reinterpret_cast<V *>(buf_psi);
+        V *tg = reinterpret_cast<V *>(buf_g);
+        for (int g = a.num_gates - 1; g >= 0; --g) {
+            const FusedGate &gd = a.gates[g];
+            const bool ng = (ba.needs_grad >> g) & 1ull;
+            const C *M = sM + gd.smoff;
+            double2 *acc = sAcc + gd.smoff;
+            const bool low = (APV == 2) && gd.sb[0] == 0;
+            if constexpr (APV == 2) {
+                if (low) {
+                    if (gd.k == 1) bwd_gate_smem<R, 1, true>(tpsi, tg, M, gd, TV, NT, ng, acc);
+                    else bwd_gate_smem<R, 2, true>(tpsi, tg, M, gd, TV, NT, ng, acc);
+                }
+            }
+            if (!low) {
+                if (gd.k == 1) bwd_gate_smem<R, 1, false>(tpsi, tg, M, gd, TV, NT, ng, acc);
+                else bwd_gate_smem<R, 2, false>(tpsi, tg, M, gd, TV, NT, ng, acc);
+            }
+            __syncthreads();
+        }
+        fence_proxy_async();
+        __syncthreads();
+        if (mover) {
+            if (a.trank > 0) {
+                if (lane == 0) {
+                    int c[5];
+                    tensor_coords(base, c);
+                    tma_store(a.trank, &a.tmap_in, c, smem_u32(buf_psi));
+                    tma_store(a.trank, &a.tmap_out, c, smem_u32(buf_g));
+                }
+            } else {
+                for (unsigned r = lane; r < runs; r += 32) {
+                    const uint64_t o = (base + run_offset(r)) * sizeof(C);
+                    bulk_s2g(gp_psi + o, smem_u32(buf_psi) + r * run_bytes, run_bytes);
+                    bulk_s2g(gp_g + o, smem_u32(buf_g) + r * run_bytes, run_bytes);
+                }
+            }
+            bulk_commit();
+        }
+    }
+    if (mover) bulk_wait_all();
+    __syncthreads();
+    // flush the gradient accumulators (entries are in register order per gate; the host shim
+    // un-permutes them)
+    if (last_row >= 0) {
+        const long long dst_row = a.mats_row_stride != 0 ? last_row : 0;
+        for (int e = threadIdx.x; e < ba.mat_elems; e += NT) {
+            const double2 v = sAcc[e];
+            atomicAdd(&ba.acc[dst_row * ba.mat_elems + e].x, v.x);
+            atomicAdd(&ba.acc[dst_row * ba.mat_elems + e].y, v.y);
+        }
+    }
+}
+
 static int max_tile_bits(int dtype) { return dtype == UA_C64 ? 14 : 13; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -758,29 +1062,29 @@ extern "C" int ua_fused_limits(int dtype, int *max_tile_bits_out, int *max_matri
     return UA_OK;
 }
 
-extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long long total_amps,
-                                   int total_bits, int tile_low_bits, int num_high,
-                                   const int *host_high_pos, int num_gates, const int *host_gate_k,
-                                   const int *host_gate_bits, const long long *host_gate_offset,
-                                   const void *gate_mats, long long gate_row_stride, int adjoint,
-                                   void *stream) {
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype != UA_C64 && dtype != UA_C128) { set_error("ua_apply_fused_pass: bad dtype"); return UA_ERR_INVALID; }
+// Validate a pass description and fill the kernel arguments shared by the forward and the
+// backward pass (geometry, gate descriptors).  max_k: largest gate the caller's kernel handles.
+static int fill_fused_args(FusedArgs &a, const char *who, int dtype, void *out, const void *in,
+                           long long total_amps, int total_bits, int tile_low_bits, int num_high,
+                           const int *host_high_pos, int num_gates, const int *host_gate_k,
+                           const int *host_gate_bits, const long long *host_gate_offset,
+                           const void *gate_mats, long long gate_row_stride, int adjoint, int max_k,
+                           int *mat_elems_out) {
+    if (dtype != UA_C64 && dtype != UA_C128) { set_error("%s: bad dtype", who); return UA_ERR_INVALID; }
     if (!out || !in || !gate_mats || !host_gate_k || !host_gate_bits || !host_gate_offset || (num_high > 0 && !host_high_pos)) {
-        set_error("ua_apply_fused_pass: null pointer"); return UA_ERR_INVALID;
+        set_error("%s: null pointer", who); return UA_ERR_INVALID;
     }
-    if (((uintptr_t)out | (uintptr_t)in) & 15) { set_error("ua_apply_fused_pass: state pointers must be 16-byte aligned"); return UA_ERR_INVALID; }
+    if (((uintptr_t)out | (uintptr_t)in) & 15) { set_error("%s: state pointers must be 16-byte aligned", who); return UA_ERR_INVALID; }
     const int L = tile_low_bits, H = num_high, T = L + H;
     const int min_low = (dtype == UA_C64) ? 1 : 0;
     if (total_bits < 1 || total_bits > 48 || L < min_low || H < 0 || T > total_bits || T > max_tile_bits(dtype)) {
-        set_error("ua_apply_fused_pass: bad tile geometry total_bits=%d L=%d H=%d", total_bits, L, H); return UA_ERR_INVALID;
+        set_error("%s: bad tile geometry total_bits=%d L=%d H=%d", who, total_bits, L, H); return UA_ERR_INVALID;
     }
-    if (num_gates < 1 || num_gates > UA_MAX_FUSED_GATES) { set_error("ua_apply_fused_pass: num_gates=%d out of range", num_gates); return UA_ERR_INVALID; }
+    if (num_gates < 1 || num_gates > UA_MAX_FUSED_GATES) { set_error("%s: num_gates=%d out of range", who, num_gates); return UA_ERR_INVALID; }
     const long long space = 1ll << total_bits;
-    if (total_amps < space || total_amps % space != 0) { set_error("ua_apply_fused_pass: total_amps must be a multiple of 2^total_bits"); return UA_ERR_INVALID; }
+    if (total_amps < space || total_amps % space != 0) { set_error("%s: total_amps must be a multiple of 2^total_bits", who); return UA_ERR_INVALID; }
     const long long rows = total_amps >> total_bits;
 
-    FusedArgs a{};
     a.in = in; a.out = out; a.mats = gate_mats; a.mats_row_stride = gate_row_stride;
     a.total_bits = total_bits; a.T = T; a.L = L; a.H = H;
     a.num_gates = num_gates; a.adjoint = adjoint ? 1 : 0;
@@ -789,7 +1093,7 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     int prev = L - 1;
     for (int i = 0; i < H; ++i) {
         const int p = host_high_pos[i];
-        if (p <= prev || p >= total_bits) { set_error("ua_apply_fused_pass: high positions must be ascending in [L, total_bits)"); return UA_ERR_INVALID; }
+        if (p <= prev || p >= total_bits) { set_error("%s: high positions must be ascending in [L, total_bits)", who); return UA_ERR_INVALID; }
         a.high[i] = p; local_of[p] = L + i; prev = p;
     }
     a.tiles_per_row = 1ll << (total_bits - T);
@@ -798,8 +1102,8 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     int mat_elems = 0;
     for (int g = 0; g < num_gates; ++g) {
         const int k = host_gate_k[g];
-        if (k < 1 || k > 3) { set_error("ua_apply_fused_pass: gate %d has k=%d (1..3 supported)", g, k); return UA_ERR_UNSUPPORTED; }
-        if (k > T) { set_error("ua_apply_fused_pass: gate %d has more qubits than the tile", g); return UA_ERR_INVALID; }
+        if (k < 1 || k > max_k) { set_error("%s: gate %d has k=%d (1..%d supported)", who, g, k, max_k); return UA_ERR_UNSUPPORTED; }
+        if (k > T) { set_error("%s: gate %d has more qubits than the tile", who, g); return UA_ERR_INVALID; }
         FusedGate &gd = a.gates[g];
         gd.k = (unsigned char)k;
         gd.goff = host_gate_offset[g];
@@ -808,15 +1112,33 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
         int lb[3], order[3];
         for (int j = 0; j < k; ++j) {
             const int p = host_gate_bits[g * 3 + j];
-            if (p < 0 || p >= total_bits || local_of[p] < 0) { set_error("ua_apply_fused_pass: gate %d bit %d is outside the tile", g, p); return UA_ERR_INVALID; }
+            if (p < 0 || p >= total_bits || local_of[p] < 0) { set_error("%s: gate %d bit %d is outside the tile", who, g, p); return UA_ERR_INVALID; }
             lb[j] = local_of[p]; order[j] = j;
-            for (int jj = 0; jj < j; ++jj) if (lb[jj] == lb[j]) { set_error("ua_apply_fused_pass: gate %d repeats a bit", g); return UA_ERR_INVALID; }
+            for (int jj = 0; jj < j; ++jj) if (lb[jj] == lb[j]) { set_error("%s: gate %d repeats a bit", who, g); return UA_ERR_INVALID; }
         }
         for (int i = 1; i < k; ++i)
             for (int j = i; j > 0 && lb[order[j]] < lb[order[j - 1]]; --j) { int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t; }
         for (int i = 0; i < k; ++i) { gd.sb[i] = (unsigned char)lb[order[i]]; gd.gb[i] = (unsigned char)(k - 1 - order[i]); }
     }
-    if (mat_elems > FUSED_MAX_MAT_ELEMS) { set_error("ua_apply_fused_pass: %d matrix elements exceed the %d limit", mat_elems, FUSED_MAX_MAT_ELEMS); return UA_ERR_INVALID; }
+    if (mat_elems > FUSED_MAX_MAT_ELEMS) { set_error("%s: %d matrix elements exceed the %d limit", who, mat_elems, FUSED_MAX_MAT_ELEMS); return UA_ERR_INVALID; }
+    *mat_elems_out = mat_elems;
+    return UA_OK;
+}
+
+extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long long total_amps,
+                                   int total_bits, int tile_low_bits, int num_high,
+                                   const int *host_high_pos, int num_gates, const int *host_gate_k,
+                                   const int *host_gate_bits, const long long *host_gate_offset,
+                                   const void *gate_mats, long long gate_row_stride, int adjoint,
+                                   void *stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    FusedArgs a{};
+    int mat_elems = 0;
+    const int rc = fill_fused_args(a, "ua_apply_fused_pass", dtype, out, in, total_amps, total_bits, tile_low_bits,
+                                   num_high, host_high_pos, num_gates, host_gate_k, host_gate_bits,
+                                   host_gate_offset, gate_mats, gate_row_stride, adjoint, 3, &mat_elems);
+    if (rc) return rc;
+    const int T = a.T;
 
     a.trank = 0;
     setup_tensor_maps(a, dtype == UA_C64 ? 0 : 1, total_amps);
@@ -841,4 +1163,53 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     if (threads == 128) return launch_fused<double, 128>(a, tile_bytes, mat_bytes, st);
     if (threads == 256) return launch_fused<double, 256>(a, tile_bytes, mat_bytes, st);
     return launch_fused<double, 512>(a, tile_bytes, mat_bytes, st);
+}
+
+extern "C" int ua_fused_backward_pass(int dtype, void *psi, void *grad, long long total_amps,
+                                      int total_bits, int tile_low_bits, int num_high,
+                                      const int *host_high_pos, int num_gates, const int *host_gate_k,
+                                      const int *host_gate_bits, const long long *host_gate_offset,
+                                      const void *gate_mats, long long gate_row_stride,
+                                      const int *host_gate_needs_grad, void *grad_acc, void *stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    BwdArgs ba{};
+    int mat_elems = 0;
+    if (!host_gate_needs_grad || !grad_acc) { set_error("ua_fused_backward_pass: null pointer"); return UA_ERR_INVALID; }
+    if (psi == grad) { set_error("ua_fused_backward_pass: psi and grad must be different buffers"); return UA_ERR_INVALID; }
+    const int rc = fill_fused_args(ba.f, "ua_fused_backward_pass", dtype, grad, psi, total_amps, total_bits,
+                                   tile_low_bits, num_high, host_high_pos, num_gates, host_gate_k,
+                                   host_gate_bits, host_gate_offset, gate_mats, gate_row_stride, 1, 2, &mat_elems);
+    if (rc) return rc;
+    ba.f.trank = 0;
+    setup_tensor_maps(ba.f, dtype == UA_C64 ? 0 : 1, total_amps);
+    ba.acc = reinterpret_cast<double2 *>(grad_acc);
+    ba.mat_elems = mat_elems;
+    ba.needs_grad = 0;
+    for (int g = 0; g < num_gates; ++g)
+        if (host_gate_needs_grad[g]) ba.needs_grad |= 1ull << g;
+    const size_t csize = (dtype == UA_C64) ? 8 : 16;
+    const size_t tile_bytes = ((size_t)1 << ba.f.T) * csize;
+    const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
+    const size_t smem = 2 * tile_bytes + mat_bytes + (size_t)mat_elems * sizeof(double2);
+    if (smem > 200 * 1024) { set_error("ua_fused_backward_pass: tile too large (%zu bytes of shared memory)", smem); return UA_ERR_UNSUPPORTED; }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_sm = 0;
+    cudaError_t e;
+    if (dtype == UA_C64) {
+        static bool set64 = false;
+        if (!set64) { cudaFuncSetAttribute(fused_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); set64 = true; }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_bwd_kernel<float>, 256, smem);
+    } else {
+        static bool set128 = false;
+        if (!set128) { cudaFuncSetAttribute(fused_bwd_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); set128 = true; }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_bwd_kernel<double>, 256, smem);
+    }
+    if (e != cudaSuccess || per_sm < 1) { set_error("ua_fused_backward_pass: occupancy query failed (%s), smem=%zu", cudaGetErrorString(e), smem); cudaGetLastError(); return UA_ERR_CUDA; }
+    long long grid = (long long)per_sm * sms;
+    if (grid > ba.f.num_tiles) grid = ba.f.num_tiles;
+    if (dtype == UA_C64) fused_bwd_kernel<float><<<(unsigned)grid, 256, smem, st>>>(ba);
+    else fused_bwd_kernel<double><<<(unsigned)grid, 256, smem, st>>>(ba);
+    return check_launch("fused_bwd_kernel");
 }

@@ -84,9 +84,34 @@ def default_geometry(num_qubits: int, dtype: torch.dtype) -> TileGeometry:
     return TileGeometry(num_qubits, tile, low, tile - low, ebits)
 
 
+def backward_geometry(num_qubits: int, dtype: torch.dtype) -> TileGeometry:
+    """Tile shape of the fused backward pass: two tiles (psi and grad) share the CTA's shared
+    memory, so the tile is one bit smaller than the forward one."""
+    geo = default_geometry(num_qubits, dtype)
+    tile = min(geo.tile_bits, (11 if dtype == torch.complex128 else 12), num_qubits)
+    low = min(geo.low_bits, tile)
+    return TileGeometry(num_qubits, tile, low, tile - low, geo.elem_bits)
+
+
+def _sorted_to_gate_index(bits):
+    """The native kernels index a gate's rows/columns in TARGET-BIT order (bit i of the index
+    <-> i-th lowest target bit position); unitair's gate index has its most significant bit on
+    qubits[0].  Returns idx with gate[gi, gj] = sorted[idx[gi], idx[gj]], or None if identical."""
+    k = len(bits)
+    order = sorted(range(k), key=lambda j: bits[j])          # ascending bit position
+    gbit = [k - 1 - order[i] for i in range(k)]              # gate-index bit of sorted bit i
+    idx = [0] * (1 << k)
+    for s_ in range(1 << k):
+        gi = 0
+        for i in range(k):
+            gi |= ((s_ >> i) & 1) << gbit[i]
+        idx[gi] = s_
+    return None if idx == list(range(1 << k)) else idx
+
+
 def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
                 max_gates: int = L.MAX_FUSED_GATES, max_mat_elems: int = 2048,
-                lookahead: int = 512) -> List[Pass]:
+                lookahead: int = 512, max_fused_k: int = MAX_FUSED_K) -> List[Pass]:
     """Cut an ordered gate list into passes.
 
     gate_bits[g] are the index-bit positions gate g acts on.  Gates are only reordered
@@ -102,7 +127,7 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             first += 1
             continue
         k0 = len(gate_bits[first])
-        if k0 > MAX_FUSED_K:
+        if k0 > max_fused_k:
             passes.append(Pass(high=[], gates=[first], direct=True))
             done[first] = True
             continue
@@ -119,7 +144,7 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
                 break
             bits = gate_bits[g]
             k = len(bits)
-            if k > MAX_FUSED_K or any(b in blocked for b in bits):
+            if k > max_fused_k or any(b in blocked for b in bits):
                 blocked.update(bits)
                 continue
             need = {b for b in bits if b >= geo.low_bits} - high
@@ -380,17 +405,65 @@ class _AdjointCircuit(torch.autograd.Function):
         n = ctx.n
         dim = 1 << n
         batch = out.numel() >> n
+        batch_shape = tuple(out.shape[:-1])
+        dev = out.device
         psi = out.clone()
         g = _engine._aligned(grad_out).clone()
         grads = [None] * len(mats)
-        for i in range(len(mats) - 1, -1, -1):
-            qs, m = ctx.qubit_lists[i], _engine._aligned(mats[i])
+        qls = ctx.qubit_lists
+        need = [bool(ctx.needs_input_grad[3 + i]) for i in range(len(mats))]
+
+        def one_gate(i):
+            qs, m = qls[i], _engine._aligned(mats[i])
             k = len(qs)
             gstride = 0 if m.dim() == 2 else 4 ** k
             _engine.launch_gate(psi, psi, m, n, k, qs, batch, dim, gstride, True)     # psi_in
-            if ctx.needs_input_grad[3 + i]:
+            if need[i]:
                 grads[i] = _engine.launch_gate_grad(g, psi, n, k, qs, batch, dim, gstride, m.shape)
             _engine.launch_gate(g, g, m, n, k, qs, batch, dim, gstride, True)         # grad wrt psi_in
+
+        if os.environ.get("UA_FUSED_BACKWARD", "1") == "0":
+            for i in range(len(mats) - 1, -1, -1):
+                one_gate(i)
+        else:
+            # fused backward passes: psi and g tiles staged together, all 1-/2-qubit gates of a
+            # pass handled in shared memory (ua_fused_backward_pass)
+            geo = backward_geometry(n, out.dtype)
+            gate_bits = [[n - 1 - q for q in qs] for qs in qls]
+            passes = plan_passes(gate_bits, geo, max_fused_k=2)
+            packed, offsets, row_stride = _pack_gates([_engine._aligned(m) for m in mats], batch_shape)
+            lib = L.lib()
+            code = L.dtype_code(out.dtype)
+            rows = batch if row_stride else 1
+            with L.on_device(dev):
+                stream = L.stream_ptr(dev)
+                for p in reversed(passes):
+                    if p.direct:
+                        one_gate(p.gates[0])
+                        continue
+                    pl = _PassLaunch(p, geo, gate_bits, offsets)
+                    ks = [len(gate_bits[gi]) for gi in p.gates]
+                    elems = sum(4 ** k for k in ks)
+                    acc = torch.zeros((rows, elems, 2), dtype=torch.float64, device=dev)
+                    flags = L.int_array([1 if need[gi] else 0 for gi in p.gates])
+                    L.check(lib.ua_fused_backward_pass(
+                        code, psi.data_ptr(), g.data_ptr(), batch << n, n, pl.low, pl.nhigh, pl.high,
+                        pl.ngates, pl.ks, pl.bits, pl.offs, packed.data_ptr(), row_stride, flags,
+                        acc.data_ptr(), stream))
+                    if any(need[gi] for gi in p.gates):
+                        accc = torch.view_as_complex(acc)            # (rows, elems) complex128
+                        off = 0
+                        for gi, k in zip(p.gates, ks):
+                            d = 1 << k
+                            if need[gi]:
+                                blk = accc[:, off:off + d * d].reshape(rows, d, d)
+                                idx = _sorted_to_gate_index(gate_bits[gi])
+                                if idx is not None:
+                                    it = torch.tensor(idx, device=dev)
+                                    blk = blk.index_select(-2, it).index_select(-1, it)
+                                gm = mats[gi]
+                                grads[gi] = blk.to(gm.dtype).reshape(gm.shape)
+                            off += d * d
         grad_state = g if ctx.needs_input_grad[0] else None
         return (grad_state, None, None, *grads)
 
@@ -435,11 +508,48 @@ def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torc
     return CompiledCircuit(gates, n, state.dtype, batch_shape).run(state, in_place=in_place)
 
 
+_ALL_QUBITS_PLANS = {}
+
+
+def _all_qubits_plan(n: int, dtype: torch.dtype):
+    """Passes for 'one 1-qubit gate on every qubit' depend only on (n, dtype, tile settings):
+    plan once, replay with whatever matrix the call brings (all gates share offset 0)."""
+    geo = default_geometry(n, dtype)
+    key = (n, dtype, geo.tile_bits, geo.low_bits)
+    plan = _ALL_QUBITS_PLANS.get(key)
+    if plan is None:
+        gate_bits = [[n - 1 - q] for q in range(n)]
+        passes = plan_passes(gate_bits, geo)
+        plan = [_PassLaunch(p, geo, gate_bits, [0] * n) for p in passes]
+        _ALL_QUBITS_PLANS[key] = plan
+    return plan
+
+
 def apply_same_gate_all_qubits(operator: torch.Tensor, state: torch.Tensor, n: int) -> torch.Tensor:
     """The same 2x2 (shared or per batch entry) on every qubit, qubit 0 first
     (src/unitair/simulation/operations.py:369-413)."""
     op_batch = tuple(operator.shape[:-2])
     st_batch = tuple(state.shape[:-1])
+    no_grad = not (torch.is_grad_enabled() and (operator.requires_grad or state.requires_grad))
+    if no_grad and state.is_complex() and operator.dtype == state.dtype and (not op_batch or op_batch == st_batch) \
+            and state.numel() > 0:
+        # fast path: cached plan, the operator itself is the matrix buffer (no packing, no merging)
+        cur = _engine._aligned(state)
+        mats = _engine._aligned(operator)
+        out = torch.empty_like(cur)
+        batch = _engine._prod(st_batch)
+        dev = cur.device
+        lib = L.lib()
+        code = L.dtype_code(cur.dtype)
+        src = cur
+        with L.on_device(dev):
+            stream = L.stream_ptr(dev)
+            for pl in _all_qubits_plan(n, cur.dtype):
+                L.check(lib.ua_apply_fused_pass(
+                    code, out.data_ptr(), src.data_ptr(), batch << n, n, pl.low, pl.nhigh, pl.high,
+                    pl.ngates, pl.ks, pl.bits, pl.offs, mats.data_ptr(), 4 if op_batch else 0, 0, stream))
+                src = out
+        return out
     if op_batch and not st_batch:
         state = state.expand(op_batch + state.shape[-1:])
     elif op_batch and op_batch != st_batch:
