@@ -56,6 +56,7 @@ struct FusedArgs {
     int swizzle;                 // 1: bank-conflict-free member swizzle for low targets
     int use_f2;                  // 1: complex64 gate phase with packed FFMA2
     int l2_prefetch;             // 1: L2-prefetch the tile this CTA will load next
+    unsigned long long *trace;   // debug: per-CTA phase timestamps (globaltimer ns), or null
     int stagger_ns;              // start delay per co-resident CTA index (breaks lockstep)
     int num_sms;
     int trank;                   // 0 = tensor path off (per-run bulk copies instead)
@@ -144,6 +145,13 @@ __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr int TRACE_TILES = 16;     // tiles traced per CTA, 4 timestamps each
+
 __device__ __forceinline__ unsigned insert_zero32(unsigned x, int p) {
     const unsigned lo = x & ((1u << p) - 1u);
     return ((x >> p) << (p + 1)) | lo;
@@ -162,7 +170,8 @@ template <typename V> __device__ __forceinline__ void cond_swap(V &a, V &b, bool
 template <typename R, int K, bool LOW, bool SWZ, bool LEAN = false>
 __device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
                                                 const typename CplxOf<R>::type *M,
-                                                const FusedGate &gd, int TV, int nthreads) {
+                                                const FusedGate &gd, int TV, int nthreads,
+                                                unsigned tid = threadIdx.x) {
     using C = typename CplxOf<R>::type;
     using V = typename VecOf<R>::type;
     constexpr int APV = VecOf<R>::APV;
@@ -202,7 +211,7 @@ __device__ __forceinline__ void apply_gate_smem(typename VecOf<R>::type *tv,
     auto Mat = [&](int s, int t) -> C { return MREG ? mr[s * D + t] : M[s * D + t]; };
 
     const unsigned groups = 1u << (TV - KH);
-    for (unsigned g0 = threadIdx.x; g0 < groups; g0 += nthreads * GU) {
+    for (unsigned g0 = tid; g0 < groups; g0 += nthreads * GU) {
         unsigned gbase[GU];
         V x[GU][NV];
         bool ok[GU];
@@ -573,6 +582,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
             const long long tn = tile_id + (long long)(nstage - 1) * step;
             if (tn < a.num_tiles) {
                 bulk_wait_read_all();
+                if (a.trace && threadIdx.x == 0 && it < TRACE_TILES) a.trace[((size_t)blockIdx.x * TRACE_TILES + it) * 4 + 3] = global_ns();
                 __syncwarp();
                 issue_load(tn, (int)((it + nstage - 1) % nstage));
             }
@@ -601,7 +611,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
             mats_loaded = true;
             __syncthreads();
         }
+        if (a.trace && threadIdx.x == 0 && it < TRACE_TILES) a.trace[((size_t)blockIdx.x * TRACE_TILES + it) * 4 + 0] = global_ns();
         mbar_wait(smem_u32(&bars[s]), parity);
+        if (a.trace && threadIdx.x == 0 && it < TRACE_TILES) a.trace[((size_t)blockIdx.x * TRACE_TILES + it) * 4 + 1] = global_ns();
         // single-buffered CTAs cannot load ahead: at least pull the next tile into L2 now so the
         // real load after this tile's store is an L2 hit
         if (a.l2_prefetch && a.trank > 0 && threadIdx.x == 0) {
@@ -622,6 +634,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
         }
         fence_proxy_async();        // make the generic-proxy writes visible to the copy engine
         __syncthreads();
+        if (a.trace && threadIdx.x == 0 && it < TRACE_TILES) a.trace[((size_t)blockIdx.x * TRACE_TILES + it) * 4 + 2] = global_ns();
         if (mover) {
             issue_store(tile_id, s);
             if (nstage >= 3) {
@@ -635,6 +648,133 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
         }
     }
     if (mover) bulk_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------
+// Team variant of the forward pass (shared gates, TMA tensor path): ONE 512-thread CTA per SM
+// split into two independent 256-thread teams that share THREE tile buffers.  Tile j of the
+// CTA's sequence is processed by team j & 1 in buffer j % 3; after a team has stored tile j
+// it refills that buffer with tile j + 3 a couple of gates into its next tile (by then the
+// store has drained), so every team always finds its next tile already in shared memory:
+// the ~3 us store drain + ~1-2 us load wait per tile (measured with ua_debug_set_fused_trace)
+// no longer idle a CTA, while the two teams still interleave their LDS and FMA phases.
+__device__ __forceinline__ void team_barrier(int team) {
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+}
+
+template <typename R>
+__global__ void __launch_bounds__(512, 1) fused_pass_team_kernel(const __grid_constant__ FusedArgs a) {
+    using C = typename CplxOf<R>::type;
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    constexpr int APVLOG = APV == 2 ? 1 : 0;
+    constexpr int NB = 3;
+    constexpr int EBITS = sizeof(C) == 8 ? 0 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long bars[NB];
+    const unsigned tile_bytes = (1u << a.T) * (unsigned)sizeof(C);
+    C *sM = reinterpret_cast<C *>(smem_raw + (size_t)NB * tile_bytes);
+    const int TV = a.T - APVLOG;
+    const int team = threadIdx.x >> 8;
+    const unsigned ttid = threadIdx.x & 255u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NB; ++s) mbar_init(smem_u32(&bars[s]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    // gate matrices -> shared memory, register order (shared by both teams)
+    {
+        const C *__restrict__ mats = reinterpret_cast<const C *>(a.mats);
+        for (int g = 0; g < a.num_gates; ++g) {
+            const FusedGate &gd = a.gates[g];
+            const int K = gd.k, D = 1 << K;
+            for (int e = threadIdx.x; e < D * D; e += 512) {
+                const int sr = e >> K, t = e & (D - 1);
+                int gi = 0, gj = 0;
+                for (int i = 0; i < K; ++i) {
+                    gi |= ((sr >> i) & 1) << gd.gb[i];
+                    gj |= ((t >> i) & 1) << gd.gb[i];
+                }
+                C val;
+                if (a.adjoint) val = cconj(mats[gd.goff + gj * D + gi]);
+                else val = mats[gd.goff + gi * D + gj];
+                sM[gd.smoff + e] = val;
+            }
+        }
+    }
+    __syncthreads();
+
+    const long long count = (a.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles of this CTA
+    auto coords_of = [&](long long j, int *c) {
+        const long long tile_id = blockIdx.x + j * (long long)gridDim.x;
+        const long long row = tile_id / a.tiles_per_row;
+        const long long jj = tile_id - row * a.tiles_per_row;
+        uint64_t base = (uint64_t)jj << a.L;
+        for (int i = 0; i < a.H; ++i) base = insert_zero(base, a.high[i]);
+        base += (uint64_t)row << a.total_bits;
+        const uint64_t e = base << EBITS;
+        for (int d = 0; d < a.trank; ++d) {
+            uint64_t v = e >> a.tstart[d];
+            if (d + 1 < a.trank) v &= (1ull << (a.tstart[d + 1] - a.tstart[d])) - 1ull;
+            c[d] = (int)v;
+        }
+    };
+    auto issue_load = [&](long long j) {          // one thread
+        const int b = (int)(j % NB);
+        const unsigned bar = smem_u32(&bars[b]);
+        int c[5];
+        coords_of(j, c);
+        mbar_arrive_expect_tx(bar, tile_bytes);
+        tma_load(a.trank, smem_u32(smem_raw + (size_t)b * tile_bytes), &a.tmap_in, c, bar);
+    };
+    if (threadIdx.x == 0)
+        for (long long j = 0; j < NB && j < count; ++j) issue_load(j);
+    __syncthreads();
+
+    long long pending = -1;                         // tile whose load waits for this team's last store
+    const int refill_after = a.num_gates >= 2 ? 1 : 0;
+    for (long long j = team; j < count; j += 2) {
+        const int b = (int)(j % NB);
+        mbar_wait(smem_u32(&bars[b]), (unsigned)((j / NB) & 1));
+        V *tv = reinterpret_cast<V *>(smem_raw + (size_t)b * tile_bytes);
+        for (int g = 0; g < a.num_gates; ++g) {
+            const FusedGate &gd = a.gates[g];
+            const C *M = sM + gd.smoff;
+            const bool low = (APV == 2) && gd.sb[0] == 0;
+            if constexpr (APV == 2) {
+                if (low) {
+                    if (gd.k == 1) apply_gate_smem<R, 1, true, false>(tv, M, gd, TV, 256, ttid);
+                    else if (gd.k == 2) apply_gate_smem<R, 2, true, false>(tv, M, gd, TV, 256, ttid);
+                    else apply_gate_smem<R, 3, true, false>(tv, M, gd, TV, 256, ttid);
+                }
+            }
+            if (!low) {
+                if (gd.k == 1) apply_gate_smem<R, 1, false, false>(tv, M, gd, TV, 256, ttid);
+                else if (gd.k == 2) apply_gate_smem<R, 2, false, false>(tv, M, gd, TV, 256, ttid);
+                else apply_gate_smem<R, 3, false, false>(tv, M, gd, TV, 256, ttid);
+            }
+            if (g == refill_after && ttid == 0 && pending >= 0) {
+                bulk_wait_read_all();               // this team's previous store has left its buffer
+                issue_load(pending);
+                pending = -1;
+            }
+            if (g + 1 < a.num_gates) team_barrier(team);
+        }
+        fence_proxy_async();
+        team_barrier(team);
+        if (ttid == 0) {
+            int c[5];
+            coords_of(j, c);
+            tma_store(a.trank, &a.tmap_out, c, smem_u32(smem_raw + (size_t)b * tile_bytes));
+            bulk_commit();
+            if (j + NB < count) pending = j + NB;
+        }
+    }
+    if (ttid == 0) {
+        if (pending >= 0) { bulk_wait_read_all(); issue_load(pending); }
+        bulk_wait_all();
+    }
 }
 
 // =======================================================================================
@@ -1006,6 +1146,8 @@ static bool setup_tensor_maps(FusedArgs &a, int ebits, long long total_amps) {
     return true;
 }
 
+static unsigned long long *g_trace_ptr = nullptr;
+
 static int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -1040,6 +1182,7 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
     a.use_f2 = env_int("UA_FUSED_F2", 0);
     a.l2_prefetch = env_int("UA_FUSED_L2PF", nstage <= 2 ? 1 : 0);
     a.stagger_ns = env_int("UA_FUSED_STAGGER_NS", 0);
+    a.trace = g_trace_ptr;
     a.num_sms = sms;
     const size_t smem = (size_t)nstage * tile_bytes + mat_bytes;
     int per_sm = 0;
@@ -1054,6 +1197,14 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
 }  // namespace ua
 
 using namespace ua;
+
+/* debug hook (not part of the public header): record per-CTA phase timestamps of the next fused
+ * passes into a device buffer of gridDim * 16 * 4 u64 (load issued / tile landed / gates done /
+ * previous store drained); null switches it off */
+extern "C" int ua_debug_set_fused_trace(void *device_buffer) {
+    g_trace_ptr = reinterpret_cast<unsigned long long *>(device_buffer);
+    return UA_OK;
+}
 
 extern "C" int ua_fused_limits(int dtype, int *max_tile_bits_out, int *max_matrix_elems_out) {
     if (dtype != UA_C64 && dtype != UA_C128) { set_error("ua_fused_limits: bad dtype"); return UA_ERR_INVALID; }
@@ -1149,6 +1300,28 @@ extern "C" int ua_apply_fused_pass(int dtype, void *out, const void *in, long lo
     // 512-thread CTA when two tiles do not fit
     // measured best (profiles/): complex64 3 x 256-thread register-lean CTAs per SM ("768"),
     // complex128 3 x 128-thread CTAs
+    // team kernel: shared gates, TMA tensor path, three tiles + matrices fit
+    // (measured equal to the 3-CTA variant, profiles/: both sit at ~78 % of the shared-memory +
+    // FMA bound of the gate phase, so it stays opt-in)
+    if (env_int("UA_FUSED_TEAM", 0) && gate_row_stride == 0 && a.trank > 0 &&
+        3 * tile_bytes + mat_bytes + 1024 <= (size_t)226 * 1024 && a.num_tiles >= 1) {
+        const size_t smem = 3 * tile_bytes + mat_bytes;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        long long grid = sms;
+        if (grid > a.num_tiles) grid = a.num_tiles;
+        if (dtype == UA_C64) {
+            static bool s64 = false;
+            if (!s64) { cudaFuncSetAttribute(fused_pass_team_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); s64 = true; }
+            fused_pass_team_kernel<float><<<(unsigned)grid, 512, smem, st>>>(a);
+        } else {
+            static bool s128 = false;
+            if (!s128) { cudaFuncSetAttribute(fused_pass_team_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); s128 = true; }
+            fused_pass_team_kernel<double><<<(unsigned)grid, 512, smem, st>>>(a);
+        }
+        return check_launch("fused_pass_team_kernel");
+    }
     int threads = env_int("UA_FUSED_THREADS", dtype == UA_C64 ? 768 : 128);
     if (threads != 512 && 2 * (tile_bytes + mat_bytes) > (size_t)222 * 1024) threads = 512;
     if (threads == 768) {     // 3 CTAs x 256 threads per SM, register-lean build
