@@ -334,6 +334,24 @@ class CompiledCircuit:
                 self._direct[pl.gate] = (_engine._aligned(m), L.int_array(qs), len(qs),
                                          0 if m.dim() == 2 else 4 ** len(qs))
 
+    def capture_graph(self, state: torch.Tensor):
+        """Capture `run(state, in_place=True)` into a CUDA graph bound to `state`'s buffer.
+
+        Small states make a deep circuit launch-bound (a pass over 2^16 amplitudes takes a few
+        microseconds, a launch from Python ~10); replaying the graph removes the host from the
+        loop.  Returns a torch.cuda.CUDAGraph; every `.replay()` applies the circuit once more
+        to the same buffer.  The state must be contiguous and 16-byte aligned.
+        """
+        if _engine._aligned(state).data_ptr() != state.data_ptr():
+            raise RuntimeError("capture_graph needs a contiguous, 16-byte aligned state")
+        # warm up outside the capture (lazy kernel attributes, tensor-map encoder lookup)
+        self.run(state, in_place=True)
+        torch.cuda.synchronize(state.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.run(state, in_place=True)
+        return graph
+
     @property
     def num_gates(self):
         return len(self.gates)

@@ -682,3 +682,25 @@ def test_multi_cz_family(ua, golden):
     w = dev(rnd_c(rng, (64,), "c128"))
     g, = torch.autograd.grad((ua.simulation.multi_cz([[0, 5]], s2) * w.conj()).real.sum(), s2)
     assert_close(host(g), orc.multi_cz([[0, 5]], host(w)), "c128")
+
+
+def test_cuda_graph_replay(ua):
+    """CompiledCircuit.capture_graph: replaying the graph equals running the circuit again."""
+    rng = np.random.default_rng(50)
+    n = 14
+    gates = []
+    for _ in range(4):
+        for q in range(n):
+            gates.append(([q], dev(haar(rng, 2, "c64"))))
+        pi = rng.permutation(n).tolist()
+        for j in range(0, n - 1, 2):
+            gates.append(([pi[j], pi[j + 1]], dev(haar(rng, 4, "c64"))))
+    cc = ua.circuit.CompiledCircuit(gates, n, torch.complex64)
+    st0 = dev(rnd_state(rng, n, (), "c64"))
+    ref = cc.run(cc.run(cc.run(st0)))                 # three applications, out of place
+    buf = st0.clone()
+    graph = cc.capture_graph(buf)                     # warm-up run applies the circuit once...
+    graph.replay()                                    # ...and two replays make three
+    graph.replay()
+    torch.cuda.synchronize()
+    assert_close(host(buf), host(ref), "c64", factor=5)
