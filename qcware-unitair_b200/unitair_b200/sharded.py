@@ -241,6 +241,35 @@ class ShardedState:
             dist.all_reduce(v, group=self.group)
         return v
 
+    def _require_identity(self, what):
+        if self.layout != identity_layout(self.n):
+            raise RuntimeError(f"{what} needs the identity qubit layout (run plans built with "
+                               f"restore=True end in it)")
+
+    def local_index_offset(self) -> int:
+        """Index of the first amplitude of this rank's shard in the full state (identity layout)."""
+        self._require_identity("local_index_offset")
+        return self.rank << self.n_local
+
+    def apply_phase(self, angles_local: torch.Tensor) -> "ShardedState":
+        """psi_k <- exp(-i angle_k) psi_k with this rank's slice of the angles (diagonal ops need no
+        communication: every rank owns a contiguous slice of the index space)."""
+        self._require_identity("apply_phase")
+        from .simulation import apply_phase
+        self.local = apply_phase(angles_local, self.local)
+        self.spare = None
+        return self
+
+    def diag_expectation_value(self, diag_local: torch.Tensor) -> torch.Tensor:
+        """sum_k d_k |psi_k|^2: local fused reduction + all_reduce of one scalar."""
+        self._require_identity("diag_expectation_value")
+        from .states import diag_expectation_value
+        v = diag_expectation_value(diag_local, self.local).to(torch.float64)
+        if self.world > 1:
+            v = v.clone()
+            dist.all_reduce(v, group=self.group)
+        return v
+
     def gather_logical(self) -> Optional[torch.Tensor]:
         """Full state in the logical (unitair) qubit order on rank 0, None elsewhere.
         Test/debug helper: needs the whole state to fit on one device."""

@@ -29,11 +29,23 @@ def main():
         sc.run(st)
         sc.run(st)                                   # replayable plan
         nrm = float(st.norm_squared())
+        # diagonal ops on the sharded state: <Z_0> and a phase layer, no communication
+        nl = n - (world.bit_length() - 1)
+        idx = torch.arange(1 << nl, device=dev) + st.local_index_offset()
+        z0 = torch.where((idx >> (n - 1)) & 1 == 0, 1.0, -1.0).to(torch.float64 if dtype == torch.complex128 else torch.float32)
+        ez = float(st.diag_expectation_value(z0))
+        ang = (idx % 97).to(z0.dtype) * 0.01
+        st.apply_phase(ang)
         got = st.gather_logical()
         if rank == 0:
             ref = ua.unit_vector(0, num_qubits=n, device=dev, dtype=dtype)
             for _ in range(2):
                 ref = ua.circuit.apply_gates(gates, ref)
+            full_idx = torch.arange(1 << n, device=dev)
+            zf = torch.where((full_idx >> (n - 1)) & 1 == 0, 1.0, -1.0).to(z0.dtype)
+            ez_ref = float(ua.diag_expectation_value(zf, ref))
+            assert abs(ez - ez_ref) < 1e-4, (ez, ez_ref)
+            ref = ua.simulation.apply_phase((full_idx % 97).to(z0.dtype) * 0.01, ref)
             err = float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt())
             assert err < tol, f"sharded vs single-GPU rel err {err}"
             assert abs(nrm - 1.0) < 1e-4, nrm
