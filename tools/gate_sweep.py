@@ -108,6 +108,21 @@ def main():
         res["abs_squared_GBs"] = round(gbs(t, 1.5 * esz * 2.0 ** n), 1)
         t = timeit(lambda: ua.inner_product(a, b))
         res["inner_product_GBs"] = round(gbs(t, 2.0 * esz * 2.0 ** n), 1)
+    if "grad" in what:
+        out = {}
+        for k, qs in ((1, [3]), (1, [n - 1]), (2, [5, 17]), (2, [n - 1, 0]), (3, [2, 9, 20])):
+            u = torch.as_tensor(haar(rng, 2 ** k).astype(npc)).to(dev)
+            t = timeit(lambda: _engine.launch_gate_grad(b, a, n, k, qs, 1, 1 << n, 0, u.shape), reps=5)
+            out[f"k{k}:{qs}"] = {"ms": round(t * 1e3, 3), "GBs": round(gbs(t, 2.0 * esz * 2 ** n), 1)}
+        res["gate_grad"] = out
+    if "permute" in what:
+        out = {}
+        for name, perm in (("swap(0,1)", [1, 0] + list(range(2, n))), ("swap(0,n-1)", [n - 1] + list(range(1, n - 1)) + [0]),
+                           ("swap(n-2,n-1)", list(range(n - 2)) + [n - 1, n - 2]), ("roll", [n - 1] + list(range(n - 1))),
+                           ("random", [int(x) for x in rng.permutation(n)])):
+            t = timeit(lambda: circuit.permute_qubits_native(perm, a, n), reps=5)
+            out[name] = {"ms": round(t * 1e3, 3), "GBs": round(gbs(t), 1)}
+        res["permute_qubits"] = out
     if "fused" in what:
         out = {}
         for tile_bits, low in ((12, 7), (13, 7), (14, 7), (13, 6), (13, 8)):
