@@ -311,7 +311,10 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     line.update(extra)
-    if world > 1:
+    big = n_local > 31          # 32+ qubits per GPU: one state copy only, no pinned host mirror
+    if big:
+        line["skipped"] = "per_gate / e2e sections need extra state copies (>= 64 GiB each): skipped at this size"
+    if world > 1 and not (big or args.no_e2e):
         # ---- end to end, sharded: every rank moves its shard from/to pinned host memory and
         # plans + runs the circuit through the public sharded API inside the timed region
         try:
@@ -350,6 +353,7 @@ def run_ours(args):
             del h_in, h_out
         except Exception as e:  # pragma: no cover
             line["e2e"] = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+    if world > 1:
         # untimed extra step with per-phase device timing (permute / exchange / gates), rank 0
         tm = {}
         plan.run(sstate, timing=tm)
@@ -358,7 +362,7 @@ def run_ours(args):
             line["nvlink_GBs_per_gpu_per_direction"] = round(
                 plan.swap_bytes_per_step / (tm["exchange"] / 1e3) / 1e9, 1)
 
-    if world == 1:
+    if world == 1 and not big:
         # ---- per-gate path (the reference's call pattern: one apply_operator per gate) ----
         psi = state
         one_layer = gates_dev[: num_gates // args.layers]
@@ -384,6 +388,7 @@ def run_ours(args):
                          "avg_launch_ms": t_pg / n_pg * 1e3}}
         del psi
 
+    if world == 1 and not (big or args.no_e2e):
         # ---- end to end through the public API with host buffers -------------------------
         try:
             h_state = torch.zeros(2 ** n_total, dtype=torch.complex64).pin_memory()
@@ -419,6 +424,7 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             line["e2e"] = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
 
+    if world == 1:
         # ---- CPU baseline (reference's own path on this box's host cores) -----------------
         if not args.no_cpu_baseline:
             try:
@@ -446,6 +452,7 @@ def main():
     ap.add_argument("--cpu-qubits", type=int, default=24,
                     help="size of the bounded CPU sample for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -330,13 +330,13 @@ __device__ __forceinline__ unsigned scatter_bits(unsigned x, const int (&vb)[KH 
 // Fast path: the tile has at least NT*GU groups (true for the production tile sizes), so there is
 // no tail predicate, the thread part of every address is computed once per gate and the group
 // part is warp-uniform.
-template <int K, bool LOW, int NT>
+template <int K, bool LOW, int NT, int VIF = 8>
 __device__ __forceinline__ void apply_gate_smem_f2(ulonglong2 *tv, const float2 *M,
                                                    const FusedGate &gd, int TV) {
     constexpr int KH = LOW ? K - 1 : K;
     constexpr int NV = 1 << KH;
     constexpr int D = 1 << K;
-    constexpr int GU = (NV >= 8) ? 1 : 8 / NV;       // 8 vectors (16 amplitudes) per thread in flight
+    constexpr int GU = (NV >= VIF) ? 1 : VIF / NV;   // VIF vectors (2 VIF amplitudes) per thread in flight
     int vb[KH > 0 ? KH : 1];
     unsigned off[KH > 0 ? KH : 1];
 #pragma unroll
@@ -352,7 +352,20 @@ __device__ __forceinline__ void apply_gate_smem_f2(ulonglong2 *tv, const float2 
 #pragma unroll
         for (int e = 0; e < D * D; ++e) mr[e] = M[e];
     }
-    auto Mat = [&](int s, int t) -> float2 { return MREG ? mr[s * D + t] : M[s * D + t]; };
+    // !MREG (3-qubit gates): the rows needed for one output vector are fetched with 16-byte
+    // broadcast loads right before they are used (D/2 LDS.128 per row)
+    float2 rowa[MREG ? 1 : D], rowb[(MREG || !LOW) ? 1 : D];
+    auto load_row = [&](float2 (&dst)[MREG ? 1 : D], int r) {
+        if constexpr (!MREG) {
+            const float4 *src = reinterpret_cast<const float4 *>(M + r * D);
+#pragma unroll
+            for (int q = 0; q < D / 2; ++q) {
+                const float4 v = src[q];
+                dst[2 * q] = make_float2(v.x, v.y);
+                dst[2 * q + 1] = make_float2(v.z, v.w);
+            }
+        }
+    };
     const f32x2_t zero = pack2(0.f, 0.f);
 
     const unsigned groups = 1u << (TV - KH);
@@ -379,9 +392,12 @@ __device__ __forceinline__ void apply_gate_smem_f2(ulonglong2 *tv, const float2 
             for (int u = 0; u < GU; ++u) { Pa[u] = zero; Qa[u] = zero; Pb[u] = zero; Qb[u] = zero; }
             if constexpr (LOW) {
                 // rows 2ov, 2ov+1; member t is half (t & 1) of vector t >> 1
+                if constexpr (!MREG) { load_row(rowa, 2 * ov); load_row(rowb, 2 * ov + 1); }
 #pragma unroll
                 for (int t = 0; t < D; ++t) {
-                    const float2 ga = Mat(2 * ov, t), gb = Mat(2 * ov + 1, t);
+                    float2 ga, gb;
+                    if constexpr (MREG) { ga = mr[(2 * ov) * D + t]; gb = mr[(2 * ov + 1) * D + t]; }
+                    else { ga = rowa[t]; gb = rowb[t]; }
                     const f32x2_t gar = pack2(ga.x, ga.x), gai = pack2(ga.y, ga.y);
                     const f32x2_t gbr = pack2(gb.x, gb.x), gbi = pack2(gb.y, gb.y);
 #pragma unroll
@@ -395,9 +411,12 @@ __device__ __forceinline__ void apply_gate_smem_f2(ulonglong2 *tv, const float2 
                 }
             } else {
                 // row ov for both amplitudes of every vector
+                if constexpr (!MREG) load_row(rowa, ov);
 #pragma unroll
                 for (int t = 0; t < D; ++t) {
-                    const float2 gm = Mat(ov, t);
+                    float2 gm;
+                    if constexpr (MREG) gm = mr[ov * D + t];
+                    else gm = rowa[t];
                     const f32x2_t gr = pack2(gm.x, gm.x), gi = pack2(gm.y, gm.y);
 #pragma unroll
                     for (int u = 0; u < GU; ++u) {
@@ -430,7 +449,11 @@ __device__ __forceinline__ void apply_gate_swz(typename VecOf<R>::type *tv,
     constexpr int KH = LOW ? K - 1 : K;
     bool swz = false;
     if constexpr (KH > 0) swz = allow_swz && ((int)gd.sb[LOW ? 1 : 0] - APVLOG) < 3;   // lowest vector-level target
-    if constexpr (LEAN) {                 // register-lean build: plain scalar path only
+    if constexpr (LEAN) {
+        // register-lean build: plain scalar path only.  (The packed-FFMA2 path was measured in
+        // this build too: same pass time -- FFMA2 halves the issue slots but occupies the FMA
+        // pipe for two cycles, and the gate phase is latency- not issue-bound; it costs spills
+        // at 80 registers, so it is not compiled in.)
         apply_gate_smem<R, K, LOW, false, true>(tv, M, gd, TV, nthreads);
         return;
     }

@@ -174,20 +174,28 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
 # --------------------------------------------------------------------------- #
 # gate merging (host bookkeeping + tiny device matmuls, no synchronisation)
 # --------------------------------------------------------------------------- #
-_SWAP_IDX = [0, 2, 1, 3]
-
-
-def _lift_to_pair(qs, m, pair):
-    """Matrix of the 1- or 2-qubit gate (qs, m) as a 4x4 on the ordered `pair`."""
-    if len(qs) == 2:
-        if list(qs) == list(pair):
-            return m
-        idx = torch.tensor(_SWAP_IDX, device=m.device)
-        return m.index_select(-2, idx).index_select(-1, idx)
-    eye = torch.eye(2, dtype=m.dtype, device=m.device)
-    if qs[0] == pair[0]:
-        return _bkron(m, eye)
-    return _bkron(eye, m)
+def _lift(qs, m, target):
+    """Matrix of the gate (qs, m) as a 2^K x 2^K operator on the ordered qubit list `target`
+    (a superset of qs): m (x) identity on the other qubits, re-indexed so that the most
+    significant index bit is target[0] (the reference's convention, operations.py:82-86)."""
+    qs, target = list(qs), list(target)
+    if qs == target:
+        return m
+    K, k = len(target), len(qs)
+    rest = [q for q in target if q not in qs]
+    full = m if not rest else _bkron(m, torch.eye(1 << len(rest), dtype=m.dtype, device=m.device))
+    order = qs + rest                      # qubit order of `full`, most significant first
+    if order == target:
+        return full
+    pos = {q: K - 1 - i for i, q in enumerate(order)}     # bit of q in full's index
+    idx = []
+    for i in range(1 << K):
+        j = 0
+        for t, q in enumerate(target):
+            j |= ((i >> (K - 1 - t)) & 1) << pos[q]
+        idx.append(j)
+    it = torch.tensor(idx, device=m.device)
+    return full.index_select(-2, it).index_select(-1, it)
 
 
 def _bkron(a, b):
@@ -198,46 +206,65 @@ def _bkron(a, b):
     return out.reshape(out.shape[:-4] + (out.shape[-4] * out.shape[-3], out.shape[-2] * out.shape[-1]))
 
 
-def merge_gates(gates):
-    """Merge neighbouring 1-/2-qubit gates into at most 2-qubit blocks.
+def default_merge_k() -> int:
+    return int(os.environ.get("UA_MERGE_MAX_K", "2"))
+
+
+def merge_gates(gates, max_k: int = None):
+    """Merge neighbouring 1-/2-qubit gates into blocks of at most `max_k` qubits.
 
     * a gate whose qubits are all covered by the most recent block on those qubits is
-      multiplied into that block;
-    * a 2-qubit gate absorbs pending 1-qubit blocks on its qubits.
-    Gates on 3+ qubits are kept as they are.  Only gates acting on disjoint qubits are
-    commuted, so the product is unchanged.  Returns a new [(qubits, matrix)] list.
+      multiplied into that block where it stands;
+    * otherwise the gate is fused with the most recent blocks on its qubits when those blocks
+      can be moved next to it (each is the LAST block on every one of its qubits) and the union
+      has at most max_k qubits; blocks that cannot join stay where they are.
+    Fusing two 2-qubit blocks that share a qubit into one 3-qubit block costs the same flops
+    (8 complex MACs per amplitude either way) and halves the shared-memory round trips of the
+    fused pass.  Gates on more than max_k qubits are kept as they are.  Only gates acting on
+    disjoint qubits are commuted, so the product is unchanged.  Returns a new
+    [(qubits, matrix)] list.
     """
+    if max_k is None:
+        max_k = default_merge_k()
+    max_k = max(2, int(max_k))
     blocks = []          # [qubits, matrix] or None when absorbed
     last = {}            # qubit -> index of the most recent block touching it
     for qs, m in gates:
         qs = list(qs)
         k = len(qs)
-        if k > 2:
+        if k > max_k:
             blocks.append([qs, m])
             for q in qs:
                 last[q] = len(blocks) - 1
             continue
-        owners = {last.get(q) for q in qs}
-        if len(owners) == 1 and None not in owners:
-            bi = owners.pop()
-            bq, bm = blocks[bi]
-            if len(bq) <= 2 and set(qs) <= set(bq):
-                if len(bq) == 1:
-                    blocks[bi][1] = torch.matmul(m, bm)
-                else:
-                    blocks[bi][1] = torch.matmul(_lift_to_pair(qs, m, bq), bm)
-                continue
-        if k == 2:
-            mat = m
-            for q in qs:
-                bi = last.get(q)
-                if bi is not None and blocks[bi] is not None and blocks[bi][0] == [q]:
-                    mat = torch.matmul(mat, _lift_to_pair([q], blocks[bi][1], qs))
-                    blocks[bi] = None
-            blocks.append([qs, mat])
-        else:
-            blocks.append([qs, m])
+        owners = []
         for q in qs:
+            bi = last.get(q)
+            if bi is not None and bi not in owners:
+                owners.append(bi)
+        # (1) covered by one block that is the most recent on all of the gate's qubits
+        if len(owners) == 1 and all(last.get(q) == owners[0] for q in qs):
+            bq, bm = blocks[owners[0]]
+            if len(bq) <= max_k and set(qs) <= set(bq):
+                blocks[owners[0]][1] = torch.matmul(_lift(qs, m, bq), bm)
+                continue
+        # (2) pull movable owner blocks into a new block at the end, smallest first
+        movable = [bi for bi in owners
+                   if len(blocks[bi][0]) <= max_k and all(last.get(q) == bi for q in blocks[bi][0])]
+        movable.sort(key=lambda bi: (len(set(blocks[bi][0]) - set(qs)), bi))
+        union = list(qs)
+        taken = []
+        for bi in movable:
+            extra = [q for q in blocks[bi][0] if q not in union]
+            if len(union) + len(extra) <= max_k:
+                union += extra
+                taken.append(bi)
+        mat = _lift(qs, m, union)
+        for bi in taken:         # the taken blocks act on disjoint qubit sets: any order
+            mat = torch.matmul(mat, _lift(blocks[bi][0], blocks[bi][1], union))
+            blocks[bi] = None
+        blocks.append([union, mat])
+        for q in union:
             last[q] = len(blocks) - 1
     return [(b[0], b[1]) for b in blocks if b is not None]
 
