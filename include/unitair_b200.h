@@ -132,6 +132,33 @@ int ua_apply_fused_pass(int dtype, void *out, const void *in, long long total_am
                         const int *host_gate_bits, const long long *host_gate_offset,
                         const void *gate_mats, long long gate_row_stride, int adjoint,
                         void *stream);
+/* Fused pass whose output is SCATTERED over 2^m destination buffers: the global-qubit exchange
+ * of a state sharded over several GPUs folded into the last pass before it (the reference is
+ * single-device; unitair_b200/sharded.py).  The m index bits host_scatter_pos[]
+ * (ascending, >= tile_low_bits, none of them a tile bit) are removed from the output index:
+ *   out_index = in_index with the scatter bits squeezed out,   buffer = value of those bits
+ * (bit j of the buffer number = index bit host_scatter_pos[j]).  host_dst_ptrs[b] is the start
+ * of destination block b (2^(total_bits-m) amplitudes) -- normally memory of a PEER GPU mapped
+ * into this process (ua_ipc_open), so the tiles travel over NVLink while the pass computes.
+ * num_gates may be 0 (pure scatter copy).  One state only (total_amps == 2^total_bits), shared
+ * gates only.  The caller orders the pass against the peers' reads (a collective barrier).    */
+#define UA_MAX_SCATTER_BITS 3
+int ua_apply_fused_pass_scatter(int dtype, const void *in, long long total_amps, int total_bits,
+                                int tile_low_bits, int num_high, const int *host_high_pos,
+                                int num_gates, const int *host_gate_k, const int *host_gate_bits,
+                                const long long *host_gate_offset, const void *gate_mats,
+                                int num_scatter_bits, const int *host_scatter_pos,
+                                void *const *host_dst_ptrs, void *stream);
+
+/* Peer memory for the scatter pass: export a device allocation of this process / map one of
+ * another process on the same node (CUDA IPC).  ua_ipc_export writes a 64-byte handle for the
+ * allocation containing `ptr` and the offset of `ptr` inside it; ua_ipc_open maps the peer's
+ * allocation and returns the address corresponding to the peer's `ptr`; ua_ipc_close unmaps
+ * (pass the pointer ua_ipc_open returned and the same offset).                                */
+int ua_ipc_export(const void *ptr, unsigned char handle_out[64], long long *offset_out);
+int ua_ipc_open(const unsigned char handle[64], long long offset, void **ptr_out);
+int ua_ipc_close(void *ptr, long long offset);
+
 /* limits of the fused pass for this dtype: largest tile (bits) and the total number of
  * complex matrix elements (sum of 4^k over the gates) one pass can hold */
 int ua_fused_limits(int dtype, int *max_tile_bits_out, int *max_matrix_elems_out);

@@ -61,8 +61,17 @@ struct FusedArgs {
     int num_sms;
     int trank;                   // 0 = tensor path off (per-run bulk copies instead)
     int tstart[6];
+    // Scatter store (global-qubit exchange folded into the pass, ua_apply_fused_pass_scatter):
+    // scatter_m index bits vpos[] (ascending, none of them a tile bit) are removed from the
+    // output index; their values select one of 2^m destination buffers (peer GPUs' memory
+    // mapped into this process).  tstart_out = tstart in the compressed index.
+    int scatter_m;
+    int vpos[UA_MAX_SCATTER_BITS];
+    int tstart_out[6];
+    void *dst[1 << UA_MAX_SCATTER_BITS];
     alignas(64) CUtensorMap tmap_in;
     alignas(64) CUtensorMap tmap_out;
+    alignas(64) CUtensorMap tmap_dst[1 << UA_MAX_SCATTER_BITS];
     FusedGate gates[UA_MAX_FUSED_GATES];
 };
 
@@ -560,10 +569,41 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
                 bulk_g2s(dst + r * run_bytes, in + (base + run_offset(r)) * sizeof(C), run_bytes, bar);
         }
     };
+    auto compress = [&](uint64_t x) -> uint64_t {      // drop the scatter bits from an index
+        for (int j = a.scatter_m - 1; j >= 0; --j) {
+            const int v = a.vpos[j];
+            x = ((x >> (v + 1)) << v) | (x & ((1ull << v) - 1ull));
+        }
+        return x;
+    };
     auto issue_store = [&](long long tile_id, int s) {  // warp 0 only
         long long row;
         const uint64_t base = tile_base(tile_id, row);
         const unsigned src = smem_u32(smem_raw + (size_t)s * tile_bytes);
+        if (a.scatter_m > 0) {
+            // the tile goes to ONE destination buffer (no scatter bit is a tile bit), at the
+            // position its index has once the scatter bits are squeezed out
+            unsigned b = 0;
+            for (int j = 0; j < a.scatter_m; ++j) b |= (unsigned)((base >> a.vpos[j]) & 1ull) << j;
+            if (a.trank > 0) {
+                if (lane == 0) {
+                    const uint64_t e = compress(base) << EBITS;
+                    int c[5];
+                    for (int j = 0; j < a.trank; ++j) {
+                        uint64_t v = e >> a.tstart_out[j];
+                        if (j + 1 < a.trank) v &= (1ull << (a.tstart_out[j + 1] - a.tstart_out[j])) - 1ull;
+                        c[j] = (int)v;
+                    }
+                    tma_store(a.trank, &a.tmap_dst[b], c, src);
+                }
+            } else {
+                char *dstp = reinterpret_cast<char *>(a.dst[b]);
+                for (unsigned r = lane; r < runs; r += 32)
+                    bulk_s2g(dstp + compress(base + run_offset(r)) * sizeof(C), src + r * run_bytes, run_bytes);
+            }
+            bulk_commit();
+            return;
+        }
         if (a.trank > 0) {
             if (lane == 0) {
                 int c[5];
@@ -1165,6 +1205,31 @@ static bool setup_tensor_maps(FusedArgs &a, int ebits, long long total_amps) {
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
     }
+    if (a.scatter_m > 0) {
+        // destination geometry: the same windows in the index with the scatter bits removed
+        // (no scatter bit lies inside a window, so every window stays contiguous)
+        const unsigned long long dst_elems = total_elems >> a.scatter_m;
+        int dstart[6];
+        for (int j = 0; j < nw; ++j) {
+            int below = 0;
+            for (int i = 0; i < a.scatter_m; ++i) below += (a.vpos[i] + ebits < wstart[j]) ? 1 : 0;
+            dstart[j] = wstart[j] - below;
+        }
+        for (int j = 0; j < nw; ++j) {
+            a.tstart_out[j] = dstart[j];
+            if (j + 1 < nw) gdim[j] = 1ull << (dstart[j + 1] - dstart[j]);
+            else gdim[j] = dst_elems >> dstart[j];
+            if (gdim[j] > 0xffffffffull || gdim[j] < box[j]) return false;
+            if (j > 0) gstride[j - 1] = (8ull << dstart[j]);
+        }
+        a.tstart_out[nw] = 0;
+        for (int b = 0; b < (1 << a.scatter_m); ++b) {
+            const CUresult r = enc(&a.tmap_dst[b], CU_TENSOR_MAP_DATA_TYPE_UINT64, (cuuint32_t)nw, a.dst[b], gdim,
+                                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return false;
+        }
+    }
     a.trank = nw;
     return true;
 }
@@ -1245,7 +1310,8 @@ static int fill_fused_args(FusedArgs &a, const char *who, int dtype, void *out, 
                            const void *gate_mats, long long gate_row_stride, int adjoint, int max_k,
                            int *mat_elems_out) {
     if (dtype != UA_C64 && dtype != UA_C128) { set_error("%s: bad dtype", who); return UA_ERR_INVALID; }
-    if (!out || !in || !gate_mats || !host_gate_k || !host_gate_bits || !host_gate_offset || (num_high > 0 && !host_high_pos)) {
+    if (!out || !in || (num_high > 0 && !host_high_pos) ||
+        (num_gates > 0 && (!gate_mats || !host_gate_k || !host_gate_bits || !host_gate_offset))) {
         set_error("%s: null pointer", who); return UA_ERR_INVALID;
     }
     if (((uintptr_t)out | (uintptr_t)in) & 15) { set_error("%s: state pointers must be 16-byte aligned", who); return UA_ERR_INVALID; }
@@ -1254,7 +1320,8 @@ static int fill_fused_args(FusedArgs &a, const char *who, int dtype, void *out, 
     if (total_bits < 1 || total_bits > 48 || L < min_low || H < 0 || T > total_bits || T > max_tile_bits(dtype)) {
         set_error("%s: bad tile geometry total_bits=%d L=%d H=%d", who, total_bits, L, H); return UA_ERR_INVALID;
     }
-    if (num_gates < 1 || num_gates > UA_MAX_FUSED_GATES) { set_error("%s: num_gates=%d out of range", who, num_gates); return UA_ERR_INVALID; }
+    if (num_gates < (max_k < 0 ? 0 : 1) || num_gates > UA_MAX_FUSED_GATES) { set_error("%s: num_gates=%d out of range", who, num_gates); return UA_ERR_INVALID; }
+    if (max_k < 0) max_k = -max_k;          // negative max_k: a pass without gates (pure copy) is allowed
     const long long space = 1ll << total_bits;
     if (total_amps < space || total_amps % space != 0) { set_error("%s: total_amps must be a multiple of 2^total_bits", who); return UA_ERR_INVALID; }
     const long long rows = total_amps >> total_bits;
@@ -1408,4 +1475,48 @@ extern "C" int ua_fused_backward_pass(int dtype, void *psi, void *grad, long lon
     if (dtype == UA_C64) fused_bwd_kernel<float><<<(unsigned)grid, 256, smem, st>>>(ba);
     else fused_bwd_kernel<double><<<(unsigned)grid, 256, smem, st>>>(ba);
     return check_launch("fused_bwd_kernel");
+}
+
+extern "C" int ua_apply_fused_pass_scatter(int dtype, const void *in, long long total_amps, int total_bits,
+                                           int tile_low_bits, int num_high, const int *host_high_pos,
+                                           int num_gates, const int *host_gate_k, const int *host_gate_bits,
+                                           const long long *host_gate_offset, const void *gate_mats,
+                                           int num_scatter_bits, const int *host_scatter_pos,
+                                           void *const *host_dst_ptrs, void *stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const char *who = "ua_apply_fused_pass_scatter";
+    if (num_scatter_bits < 1 || num_scatter_bits > UA_MAX_SCATTER_BITS || !host_scatter_pos || !host_dst_ptrs) {
+        set_error("%s: num_scatter_bits=%d out of range (1..%d) or null pointer", who, num_scatter_bits, UA_MAX_SCATTER_BITS);
+        return UA_ERR_INVALID;
+    }
+    if (total_amps != (1ll << total_bits)) { set_error("%s: one state only (total_amps must be 2^total_bits)", who); return UA_ERR_INVALID; }
+    FusedArgs a{};
+    int mat_elems = 0;
+    // `out` is only validated for alignment: pass the first destination
+    const int rc = fill_fused_args(a, who, dtype, host_dst_ptrs[0], in, total_amps, total_bits, tile_low_bits,
+                                   num_high, host_high_pos, num_gates, host_gate_k, host_gate_bits,
+                                   host_gate_offset, gate_mats, 0, 0, -3, &mat_elems);
+    if (rc) return rc;
+    a.scatter_m = num_scatter_bits;
+    for (int j = 0; j < num_scatter_bits; ++j) {
+        const int v = host_scatter_pos[j];
+        if (v < a.L || v >= total_bits || (j > 0 && v <= host_scatter_pos[j - 1])) {
+            set_error("%s: scatter positions must be ascending in [tile_low_bits, total_bits)", who); return UA_ERR_INVALID;
+        }
+        for (int i = 0; i < a.H; ++i)
+            if (a.high[i] == v) { set_error("%s: scatter bit %d is a tile bit", who, v); return UA_ERR_INVALID; }
+        a.vpos[j] = v;
+    }
+    if (a.T > total_bits - num_scatter_bits) { set_error("%s: tile larger than the destination blocks", who); return UA_ERR_INVALID; }
+    for (int b = 0; b < (1 << num_scatter_bits); ++b) {
+        if (!host_dst_ptrs[b] || ((uintptr_t)host_dst_ptrs[b] & 15)) { set_error("%s: destination %d is null or misaligned", who, b); return UA_ERR_INVALID; }
+        a.dst[b] = host_dst_ptrs[b];
+    }
+    a.trank = 0;
+    setup_tensor_maps(a, dtype == UA_C64 ? 0 : 1, total_amps);
+    const size_t csize = (dtype == UA_C64) ? 8 : 16;
+    const size_t tile_bytes = ((size_t)1 << a.T) * csize;
+    const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
+    if (dtype == UA_C64) return launch_fused<float, 256, 3>(a, tile_bytes, mat_bytes, st);
+    return launch_fused<double, 128>(a, tile_bytes, mat_bytes, st);
 }

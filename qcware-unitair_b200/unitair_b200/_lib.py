@@ -76,12 +76,19 @@ def _declare(L):
     L.ua_fused_backward_pass.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                          p_int, c_int, p_int, p_int, p_ll, c_void_p, c_longlong,
                                          p_int, c_void_p, c_void_p]
+    L.ua_apply_fused_pass_scatter.argtypes = [c_int, c_void_p, c_longlong, c_int, c_int, c_int, p_int,
+                                              c_int, p_int, p_int, p_ll, c_void_p, c_int, p_int,
+                                              POINTER(c_void_p), c_void_p]
+    L.ua_ipc_export.argtypes = [c_void_p, c_void_p, p_ll]
+    L.ua_ipc_open.argtypes = [c_void_p, c_longlong, POINTER(c_void_p)]
+    L.ua_ipc_close.argtypes = [c_void_p, c_longlong]
     L.ua_permute_bits.argtypes = [c_int, c_void_p, c_void_p, c_int, c_longlong, p_int, c_void_p]
     L.ua_apply_sign_masks.argtypes = [c_int, c_void_p, c_void_p, c_int, c_longlong, c_int,
                                       POINTER(c_ulonglong), c_void_p]
     for name in ("ua_apply_sign_masks", "ua_apply_gate", "ua_gate_grad", "ua_apply_phase", "ua_phase_backward",
                  "ua_abs_squared", "ua_norm_squared", "ua_diag_expectation", "ua_inner_product",
-                 "ua_fused_limits", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits"):
+                 "ua_fused_limits", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits",
+                 "ua_apply_fused_pass_scatter", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close"):
         getattr(L, name).restype = c_int
 
 
@@ -150,6 +157,29 @@ def int_array(values):
 
 def ll_array(values):
     return (c_longlong * len(values))(*values)
+
+
+def ptr_array(values):
+    return (c_void_p * len(values))(*values)
+
+
+def ipc_export(ptr: int):
+    """(64-byte handle, offset) naming the device allocation that contains `ptr`."""
+    buf = ctypes.create_string_buffer(64)
+    off = c_longlong(0)
+    check(lib().ua_ipc_export(c_void_p(ptr), buf, ctypes.byref(off)))
+    return bytes(buf.raw), int(off.value)
+
+
+def ipc_open(handle: bytes, offset: int) -> int:
+    out = c_void_p(0)
+    buf = ctypes.create_string_buffer(handle, 64)
+    check(lib().ua_ipc_open(buf, offset, ctypes.byref(out)))
+    return int(out.value)
+
+
+def ipc_close(ptr: int, offset: int):
+    check(lib().ua_ipc_close(c_void_p(ptr), offset))
 
 
 def workspace(nbytes: int, device):

@@ -286,6 +286,9 @@ class _PassLaunch:
         self.nhigh = len(p.high)
         self.high = L.int_array(p.high) if p.high else None
         self.ngates = len(p.gates)
+        if not p.gates:                      # pure copy pass (scatter tail without gates)
+            self.ks = self.bits = self.offs = None
+            return
         self.ks = L.int_array([len(gate_bits[g]) for g in p.gates])
         flat = []
         for g in p.gates:
@@ -400,16 +403,21 @@ class CompiledCircuit:
             raise RuntimeError("in_place=True needs a contiguous, 16-byte aligned state")
         if not self.launches or self.batch == 0:
             return cur if in_place else cur.clone()
-        dev = cur.device
         out = cur if in_place else torch.empty_like(cur)
-        src = cur
+        self._run_launches(self.launches, cur, out)
+        return out
+
+    def _run_launches(self, launches, src, out):
+        """Enqueue `launches`: the first reads `src`, all write (and later ones read) `out`."""
+        n = self.n
+        dev = out.device
         lib = L.lib()
         code = L.dtype_code(self.dtype)
         total = self.batch << n
         with L.on_device(dev):
             stream = L.stream_ptr(dev)
             mats_ptr = self.mats.data_ptr()
-            for pl in self.launches:
+            for pl in launches:
                 if pl.direct:
                     m, qarr, k, gstride = self._direct[pl.gate]
                     L.check(lib.ua_apply_gate(code, out.data_ptr(), src.data_ptr(), m.data_ptr(), n, k,
@@ -419,7 +427,84 @@ class CompiledCircuit:
                         code, out.data_ptr(), src.data_ptr(), total, n, pl.low, pl.nhigh, pl.high,
                         pl.ngates, pl.ks, pl.bits, pl.offs, mats_ptr, self.row_stride, 0, stream))
                 src = out
-        return out
+
+
+def _fill_high(high, geo: TileGeometry, forbidden=()):
+    """Complete `high` to geo.max_high positions, preferring positions that keep the number of
+    TMA windows low; positions in `forbidden` are never used.  Returns None if impossible."""
+    high = set(high)
+    while len(high) < geo.max_high:
+        free = [p for p in range(geo.low_bits, geo.total_bits) if p not in high and p not in forbidden]
+        if not free:
+            return None
+        best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits), p))
+        high.add(best)
+    return sorted(high)
+
+
+class ScatterTail:
+    """The last pass of a compiled circuit re-planned so that its tiles avoid the index bits
+    that are about to leave the shard (`victim_bits`): its output can then be stored straight
+    into the peers' buffers (ua_apply_fused_pass_scatter).  If the circuit's own last pass
+    cannot be used (it touches a victim bit, is a direct big-gate launch, or there is no
+    circuit) the tail is a pure copy pass."""
+
+    def __init__(self, compiled, n: int, dtype, victim_bits):
+        vs = sorted(int(v) for v in victim_bits)
+        m = len(vs)
+        base = default_geometry(n, dtype)
+        self.victims = L.int_array(vs)
+        self.m = m
+        self.n = n
+        self.dtype = dtype
+        self.compiled = compiled
+        self.inplace_launches = list(compiled.launches) if compiled is not None else []
+        self.reused = False
+        launch = None
+        if compiled is not None and compiled.launches and not compiled.passes[-1].direct \
+                and compiled.geo.tile_bits <= n - m and compiled.batch == 1 and compiled.row_stride == 0:
+            last = compiled.passes[-1]
+            used = {b for g in last.gates for b in compiled.gate_bits[g]}
+            if not (used & set(vs)) and min(vs) >= compiled.geo.low_bits:
+                high = _fill_high({b for b in used if b >= compiled.geo.low_bits}, compiled.geo, vs)
+                if high is not None:
+                    launch = _PassLaunch(Pass(high=high, gates=list(last.gates)), compiled.geo,
+                                         compiled.gate_bits, compiled.offsets)
+                    self.inplace_launches = self.inplace_launches[:-1]
+                    self.reused = True
+        if launch is None:
+            tile = min(base.tile_bits, n - m)
+            low = min(base.low_bits, tile)
+            if min(vs) < low:
+                raise ValueError(f"scatter bits {vs} must not be among the low {low} index bits")
+            geo = TileGeometry(n, tile, low, tile - low, base.elem_bits)
+            high = _fill_high(set(), geo, vs)
+            if high is None:
+                raise ValueError("no room for a scatter tile")
+            launch = _PassLaunch(Pass(high=high, gates=[]), geo, [], [])
+        self.launch = launch
+
+    @property
+    def num_passes(self):
+        return len(self.inplace_launches) + 1
+
+    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None):
+        """In-place passes on `state`, then the tail pass from `state` into the 2^m destination
+        blocks `dst_ptrs` (device addresses, possibly of peer GPUs).  `before_scatter` is called
+        right before the scatter pass is enqueued (cross-rank fence when the destinations may
+        still be in use)."""
+        cc = self.compiled
+        if self.inplace_launches:
+            cc._run_launches(self.inplace_launches, state, state)
+        if before_scatter is not None:
+            before_scatter()
+        pl = self.launch
+        dev = state.device
+        with L.on_device(dev):
+            L.check(L.lib().ua_apply_fused_pass_scatter(
+                L.dtype_code(self.dtype), state.data_ptr(), 1 << self.n, self.n, pl.low, pl.nhigh, pl.high,
+                pl.ngates, pl.ks, pl.bits, pl.offs, cc.mats.data_ptr() if pl.ngates else None,
+                self.m, self.victims, L.ptr_array(list(dst_ptrs)), L.stream_ptr(dev)))
 
 
 class _AdjointCircuit(torch.autograd.Function):

@@ -23,6 +23,7 @@ The planning code is pure host logic and is exercised on CPU with the gloo backe
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -39,6 +40,7 @@ class Epoch:
     incoming: List[int] = field(default_factory=list)   # logical qubits becoming local
     victims: List[int] = field(default_factory=list)    # logical qubits becoming global
     rank_bits: List[int] = field(default_factory=list)  # rank bit index each pair swaps
+    victim_bits: List[int] = field(default_factory=list)  # physical bits of the victims BEFORE perm_src
     perm_src: Optional[List[int]] = None                # local bit permutation before the exchange
     gates: List[int] = field(default_factory=list)      # gate indices executed after it
     local_bits: List[List[int]] = field(default_factory=list)  # physical bit positions per gate
@@ -51,12 +53,15 @@ def identity_layout(n: int) -> List[int]:
 
 def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
                 layout: Optional[List[int]] = None, restore: bool = True,
-                lookahead: int = 4096) -> Tuple[List[Epoch], List[int]]:
+                lookahead: int = 4096, min_victim_bit: int = 0) -> Tuple[List[Epoch], List[int]]:
     """Cut a gate list into epochs for a state sharded over 2^g ranks.
 
     layout[q] is the physical bit of logical qubit q; bits >= n-g are rank bits.  Returns the
     epochs and the final layout.  With restore=True a last exchange puts the layout back to
     the one the plan started from, so the same plan can be replayed step after step.
+    min_victim_bit: victims are only taken from physical bits >= this (the fused scatter
+    exchange keeps the low bits of every tile together; restore exchanges may still have to
+    evict a lower bit, those fall back to permute + send/recv).
     """
     n_local = n - g
     phys = list(layout) if layout is not None else identity_layout(n)
@@ -82,7 +87,8 @@ def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
     def make_exchange(incoming: List[int], victims: List[int]) -> Epoch:
         """Swap `incoming` (global) with `victims` (local); updates phys."""
         m = len(incoming)
-        ep = Epoch(incoming=list(incoming), victims=list(victims))
+        ep = Epoch(incoming=list(incoming), victims=list(victims),
+                   victim_bits=[phys[v] for v in victims])
         # victims must sit on the top m local bits: victim j -> local bit n_local - m + j
         want = {v: n_local - m + j for j, v in enumerate(victims)}
         qubit_at = {phys[q]: q for q in range(n) if phys[q] < n_local}
@@ -118,7 +124,9 @@ def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
         incoming = globals_needed[:g]
         # Belady: evict the local qubits whose next use is farthest away
         never = len(remaining) + 1
-        local_qubits = [q for q in range(n) if phys[q] < n_local]
+        local_qubits = [q for q in range(n) if min_victim_bit <= phys[q] < n_local]
+        if len(local_qubits) < len(incoming):
+            local_qubits = [q for q in range(n) if phys[q] < n_local]
         local_qubits.sort(key=lambda q: (-first_use.get(q, never), -phys[q]))
         victims = local_qubits[:len(incoming)]
         victims.sort(key=lambda q: phys[q])
@@ -160,6 +168,22 @@ def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
     return epochs, phys
 
 
+def exchange_block_id(rank: int, ep: Epoch) -> int:
+    """This rank's own value of the rank bits the exchange `ep` swaps (bit j <-> rank_bits[j])."""
+    a = 0
+    for j, rb in enumerate(ep.rank_bits):
+        a |= ((rank >> rb) & 1) << j
+    return a
+
+
+def exchange_peer(rank: int, ep: Epoch, b: int) -> int:
+    """The rank that differs from `rank` only in the swapped rank bits, which take the value b."""
+    peer = rank
+    for j, rb in enumerate(ep.rank_bits):
+        peer = (peer & ~(1 << rb)) | (((b >> j) & 1) << rb)
+    return peer
+
+
 # --------------------------------------------------------------------------- #
 # local engines
 # --------------------------------------------------------------------------- #
@@ -180,6 +204,30 @@ class CudaEngine:
 
     def num_passes(self, compiled):
         return compiled.num_passes if compiled is not None else 0
+
+    # fused scatter exchange (peer-memory stores from the last pass of an epoch)
+    supports_scatter = True
+
+    def min_victim_bit(self, n_local, g):
+        from . import circuit
+        geo = circuit.default_geometry(n_local, self.dtype)
+        return min(geo.low_bits, max(0, n_local - g))
+
+    def scatter_tail(self, compiled, n_local, victim_bits):
+        from . import circuit
+        return circuit.ScatterTail(compiled, n_local, self.dtype, victim_bits)
+
+    def run_scatter(self, tail, st, ep, before_scatter=None):
+        """The epoch's passes with the last one storing into the peers' spare buffers: block b of
+        the exchange `ep` goes to block a (this rank's own value of the swapped rank bits) of the
+        spare buffer of the rank whose swapped rank bits equal b."""
+        peers = st.peer_pointers()
+        m = len(ep.incoming)
+        block_bytes = (1 << (st.n_local - m)) * st.local.element_size()
+        a = exchange_block_id(st.rank, ep)
+        spare_of = peers[st._spare().data_ptr()]
+        dst = [spare_of[exchange_peer(st.rank, ep, b)] + a * block_bytes for b in range(1 << m)]
+        tail.run(st.local, dst, before_scatter=before_scatter)
 
     def permute(self, src_bits, shard, out):
         from . import _lib as L
@@ -228,6 +276,43 @@ class ShardedState:
         if self.spare is None:
             self.spare = torch.empty_like(self.local)
         return self.spare
+
+    # -- peer memory: every rank maps the two buffers of every other rank (CUDA IPC) ---------
+    def peer_pointers(self):
+        """{my buffer address: [address of the same buffer on rank r, as mapped into this
+        process]} for the two buffers (state, spare).  Collective: all ranks call it together.
+        The mapping is cached until one of the buffers is replaced."""
+        from . import _lib as L
+        spare = self._spare()
+        key = (self.local.data_ptr(), spare.data_ptr())
+        cache = getattr(self, "_peers", None)
+        if cache is not None and set(cache["key"]) == set(key):
+            return cache["map"]
+        self.release_peers()
+        mine = [L.ipc_export(ptr) for ptr in key]                   # [(handle, offset)] x 2
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        opened = {}                  # (rank, handle) -> base address of the mapping (small
+        #                              buffers may share one allocation: map it once)
+        table = {key[0]: [0] * self.world, key[1]: [0] * self.world}
+        for r, entries in enumerate(everyone):
+            for which, (handle, offset) in enumerate(entries):
+                if r == self.rank:
+                    table[key[which]][r] = key[which]
+                else:
+                    if (r, handle) not in opened:
+                        opened[(r, handle)] = L.ipc_open(handle, 0)
+                    table[key[which]][r] = opened[(r, handle)] + offset
+        self._peers = {"key": key, "map": table, "opened": list(opened.values())}
+        return table
+
+    def release_peers(self):
+        from . import _lib as L
+        cache = getattr(self, "_peers", None)
+        if cache is not None:
+            for base in cache["opened"]:
+                L.ipc_close(base, 0)
+            self._peers = None
 
     # -- reductions: local fused reduce + all_reduce of scalars ------------------------------
     def norm_squared(self) -> torch.Tensor:
@@ -293,7 +378,7 @@ class ShardedCircuit:
     (the plan ends in the layout it started from)."""
 
     def __init__(self, gates, num_qubits: int, dtype, world: int, engine=None,
-                 layout: Optional[List[int]] = None, restore: bool = True):
+                 layout: Optional[List[int]] = None, restore: bool = True, exchange: Optional[str] = None):
         g = world.bit_length() - 1
         if 1 << g != world:
             raise ValueError("world size must be a power of two")
@@ -308,17 +393,38 @@ class ShardedCircuit:
             if len(qs) > self.n_local:
                 raise ValueError("a gate cannot act on more qubits than are local to a rank")
         self.start_layout = list(layout) if layout is not None else identity_layout(num_qubits)
+        # exchange mode: "p2p" = the last pass before an exchange stores its tiles straight into
+        # the peers' buffers (fused compute + exchange over NVLink peer memory); "nccl" = bit
+        # permutation pass + grouped send/recv
+        if exchange is None:
+            exchange = os.environ.get("UA_EXCHANGE", "p2p")
+        self.p2p = (exchange == "p2p" and world > 1 and getattr(self.engine, "supports_scatter", False))
+        min_victim = self.engine.min_victim_bit(self.n_local, g) if self.p2p else 0
         self.epochs, self.end_layout = plan_epochs([qs for qs, _ in self.gates], num_qubits, g,
-                                                   self.start_layout, restore=restore)
+                                                   self.start_layout, restore=restore,
+                                                   min_victim_bit=min_victim)
         nl = self.n_local
         self.compiled = []
         for ep in self.epochs:
             local_gates = [([nl - 1 - p for p in bits], self.gates[gi][1])
                            for gi, bits in zip(ep.gates, ep.local_bits)]
             self.compiled.append(self.engine.compile(local_gates, nl))
+        # scatter tails: epoch i ends with the exchange that opens epoch i+1
+        self.tails = [None] * len(self.epochs)
+        if self.p2p:
+            for i in range(len(self.epochs) - 1):
+                nxt = self.epochs[i + 1]
+                if nxt.incoming and min(nxt.victim_bits) >= min_victim:
+                    self.tails[i] = self.engine.scatter_tail(self.compiled[i], nl, nxt.victim_bits)
         self.num_swaps = sum(1 for ep in self.epochs if ep.incoming)
-        self.num_passes = (sum(self.engine.num_passes(c) for c in self.compiled)
-                           + sum(1 for ep in self.epochs if ep.perm_src is not None))
+        self.num_fused_swaps = sum(1 for t in self.tails if t is not None)
+        self.num_passes = 0
+        for i, ep in enumerate(self.epochs):
+            fused_in = i > 0 and self.tails[i - 1] is not None
+            if ep.perm_src is not None and not fused_in:
+                self.num_passes += 1
+            self.num_passes += (self.tails[i].num_passes if self.tails[i] is not None
+                                else self.engine.num_passes(self.compiled[i]))
         esz = 8 if dtype == torch.complex64 else 16
         self.swap_bytes_per_step = sum(
             (esz << nl) - ((esz << nl) >> len(ep.incoming)) for ep in self.epochs if ep.incoming)
@@ -330,16 +436,12 @@ class ShardedCircuit:
         block = 1 << (nl - m)
         src = st.local
         dst = st._spare()
-        a = 0
-        for j, rb in enumerate(ep.rank_bits):
-            a |= ((st.rank >> rb) & 1) << j
+        a = exchange_block_id(st.rank, ep)
         ops = []
         for b in range(1 << m):
             if b == a:
                 continue
-            peer = st.rank
-            for j, rb in enumerate(ep.rank_bits):
-                peer = (peer & ~(1 << rb)) | (((b >> j) & 1) << rb)
+            peer = exchange_peer(st.rank, ep, b)
             # real views: complex dtypes are not supported by every backend (gloo)
             send = torch.view_as_real(src[b * block:(b + 1) * block])
             recv = torch.view_as_real(dst[b * block:(b + 1) * block])
@@ -350,6 +452,13 @@ class ShardedCircuit:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         st.local, st.spare = dst, src
+
+    def _fence(self, st: ShardedState):
+        """All ranks' scatter passes are complete (stream-ordered: a tiny all-reduce queued behind
+        each rank's pass cannot finish before every rank has reached it)."""
+        if getattr(st, "_fence_buf", None) is None:
+            st._fence_buf = torch.zeros(1, dtype=torch.float32, device=st.local.device)
+        dist.all_reduce(st._fence_buf, group=st.group)
 
     def run(self, st: ShardedState, timing: Optional[dict] = None) -> ShardedState:
         """Execute the plan.  With `timing` (a dict) and a CUDA shard, per-phase device times
@@ -367,15 +476,36 @@ class ShardedCircuit:
                 marks.append((tag, ev))
 
         mark("start")
-        for ep, comp in zip(self.epochs, self.compiled):
-            if ep.perm_src is not None:
-                out = self.engine.permute(ep.perm_src, st.local, st._spare())
-                st.local, st.spare = out, st.local
-                mark("permute")
-            if ep.incoming:
-                self._exchange(st, ep)
+        # A scatter pass writes into the peers' spare buffers.  That is safe without further
+        # synchronisation only if every peer is known to be past its last use of that buffer:
+        # true right after a fenced flip (the buffer was the peer's state until its own scatter
+        # pass, which completed before the fence), not at the start of a run or after a local
+        # permutation / send-recv exchange -- then a fence goes in front of the scatter pass.
+        spare_idle = False
+        for i, (ep, comp) in enumerate(zip(self.epochs, self.compiled)):
+            if i > 0 and self.tails[i - 1] is not None:
+                # the previous epoch's last pass already delivered this exchange into every
+                # rank's spare buffer: wait until all ranks have finished writing, then flip
+                self._fence(st)
+                st.local, st.spare = st.spare, st.local
+                spare_idle = True
                 mark("exchange")
-            self.engine.run(comp, st.local)
+            else:
+                if ep.perm_src is not None:
+                    out = self.engine.permute(ep.perm_src, st.local, st._spare())
+                    st.local, st.spare = out, st.local
+                    spare_idle = False
+                    mark("permute")
+                if ep.incoming:
+                    self._exchange(st, ep)
+                    spare_idle = False
+                    mark("exchange")
+            tail = self.tails[i]
+            if tail is not None:
+                self.engine.run_scatter(tail, st, self.epochs[i + 1],
+                                        before_scatter=None if spare_idle else (lambda: self._fence(st)))
+            else:
+                self.engine.run(comp, st.local)
             mark("gates")
         st.layout = list(self.end_layout)
         if marks:

@@ -22,10 +22,17 @@ def main():
     dev = torch.device("cuda", local_rank)
     dist.init_process_group("nccl", device_id=dev)
     world, rank = dist.get_world_size(), dist.get_rank()
-    for dtype, npc, tol in ((torch.complex64, np.complex64, 2e-5), (torch.complex128, np.complex128, 1e-11)):
+    modes = sys.argv[3].split(",") if len(sys.argv) > 3 else ["p2p", "nccl"]
+    import itertools
+    for (dtype, npc, tol), mode in itertools.product(
+            ((torch.complex64, np.complex64, 2e-5), (torch.complex128, np.complex128, 1e-11)), modes):
         gates = [(qs, torch.as_tensor(u.astype(npc)).to(dev)) for qs, u in random_circuit(n, layers, 11)]
         st = sharded.ShardedState.zero_state(n, dtype, dev)
-        sc = sharded.ShardedCircuit(gates, n, dtype, world)
+        sc = sharded.ShardedCircuit(gates, n, dtype, world, exchange=mode)
+        if mode == "p2p":
+            assert sc.num_fused_swaps > 0, "the peer-memory exchange path was not planned"
+        else:
+            assert sc.num_fused_swaps == 0
         sc.run(st)
         sc.run(st)                                   # replayable plan
         nrm = float(st.norm_squared())
@@ -49,7 +56,9 @@ def main():
             err = float((got - ref).abs().pow(2).sum().sqrt() / ref.abs().pow(2).sum().sqrt())
             assert err < tol, f"sharded vs single-GPU rel err {err}"
             assert abs(nrm - 1.0) < 1e-4, nrm
-            print(f"OK dtype={dtype} world={world} n={n} err={err:.2e} swaps={sc.num_swaps} passes={sc.num_passes}")
+            print(f"OK dtype={dtype} mode={mode} world={world} n={n} err={err:.2e} swaps={sc.num_swaps} "
+                  f"fused_swaps={sc.num_fused_swaps} passes={sc.num_passes}")
+        st.release_peers()
     dist.destroy_process_group()
 
 

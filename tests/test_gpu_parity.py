@@ -704,3 +704,86 @@ def test_cuda_graph_replay(ua):
     graph.replay()
     torch.cuda.synchronize()
     assert_close(host(buf), host(ref), "c64", factor=5)
+
+
+# --------------------------------------------------------------------------- scatter tail
+def _scatter_reference(ref, n, victims):
+    """Where ua_apply_fused_pass_scatter puts amplitude i: block = values of the victim bits,
+    offset = index with the victim bits squeezed out."""
+    idx = torch.arange(1 << n, device=ref.device)
+    block = torch.zeros_like(idx)
+    for j, v in enumerate(victims):
+        block |= ((idx >> v) & 1) << j
+    off = idx.clone()
+    for v in sorted(victims, reverse=True):
+        off = ((off >> (v + 1)) << v) | (off & ((1 << v) - 1))
+    out = torch.empty_like(ref)
+    out[block * (1 << (n - len(victims))) + off] = ref
+    return out
+
+
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("n,victims", [(16, [9]), (18, [8, 15]), (19, [7, 12, 18]), (15, [14]), (12, [10, 11])])
+def test_fused_pass_scatter_matches_permute_and_split(ua, dt, n, victims):
+    """The pass that folds a global-qubit exchange into the last fused pass (peer-memory
+    stores): with all destinations in local memory it must equal circuit + bit permutation
+    (pure data movement after the gates: bit-exact against the in-place circuit)."""
+    from unitair_b200 import circuit
+    rng = np.random.default_rng(n * 7 + len(victims))
+    st = dev(rnd_state(rng, n, (), dt))
+    low = circuit.default_geometry(n, CD[dt]).low_bits
+    victims = [v for v in victims if v >= low] or [n - 1]
+    m = len(victims)
+    block_bytes = (1 << (n - m)) * st.element_size()
+
+    def gates_avoiding(avoid, count):
+        gl = []
+        free = [q for q in range(n) if (n - 1 - q) not in avoid]
+        for _ in range(count):
+            a, b = rng.choice(free, 2, replace=False)
+            gl.append(([int(a), int(b)], dev(haar(rng, 4, dt))))
+            gl.append(([int(rng.choice(free))], dev(haar(rng, 2, dt))))
+        return gl
+
+    cases = {
+        "no circuit (pure scatter copy)": None,
+        "last pass reusable": gates_avoiding(set(victims), 6),
+        "last pass touches a victim bit (extra copy pass)":
+            gates_avoiding(set(), 5) + [([n - 1 - victims[0], (n - 1 - victims[0] + 1) % n], dev(haar(rng, 4, dt)))],
+    }
+    for name, gl in cases.items():
+        cc = circuit.CompiledCircuit(gl, n, CD[dt]) if gl else None
+        ref = cc.run(st) if cc is not None else st
+        tail = circuit.ScatterTail(cc, n, CD[dt], victims)
+        if name == "last pass reusable" and cc.geo.tile_bits <= n - m:
+            assert tail.reused, "a last pass that avoids the victim bits must be reused"
+        out = torch.full_like(st, float("nan"))
+        work = st.clone()
+        tail.run(work, [out.data_ptr() + b * block_bytes for b in range(1 << m)])
+        torch.cuda.synchronize()
+        want = _scatter_reference(ref, n, victims)
+        if tail.reused:      # same gates, different tile shape: rounding may differ in the last pass
+            assert_close(host(out), host(want), dt, what=name)
+        else:
+            assert torch.equal(torch.view_as_real(out), torch.view_as_real(want)), name
+
+
+def test_fused_pass_scatter_rejects_bad_arguments(ua):
+    from unitair_b200 import _lib as L
+    n = 14
+    st = torch.zeros(1 << n, dtype=torch.complex64, device="cuda")
+    out = torch.zeros_like(st)
+    half = (1 << (n - 1)) * 8
+    dst = L.ptr_array([out.data_ptr(), out.data_ptr() + half])
+    lib = L.lib()
+    stream = L.stream_ptr(st.device)
+
+    def call(low, high, victims, total=1 << n):
+        return lib.ua_apply_fused_pass_scatter(0, st.data_ptr(), total, n, low, len(high), L.int_array(high) if high else None,
+                                               0, None, None, None, None, len(victims), L.int_array(victims), dst, stream)
+    assert call(7, [7, 8, 9, 10, 11, 12], [13]) == 0
+    assert call(7, [7, 8, 9, 10, 11, 13], [13]) != 0        # scatter bit inside the tile
+    assert call(7, [8, 9, 10], [3]) != 0                    # scatter bit among the low bits
+    assert call(7, [7, 8, 9, 10, 11, 12, 13], [6]) != 0
+    assert call(7, [7, 8], [13], total=2 << n) != 0         # one state only
+    torch.cuda.synchronize()

@@ -20,4 +20,4 @@ def test_sharded_matches_single_gpu(world):
            os.path.join(ROOT, "tests", "_sharded_gpu_worker.py"), "20", "4"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert out.stdout.count("OK dtype") == 2, out.stdout[-2000:]
+    assert out.stdout.count("OK dtype") == 4, out.stdout[-2000:]
