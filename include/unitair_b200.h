@@ -141,14 +141,17 @@ int ua_apply_fused_pass(int dtype, void *out, const void *in, long long total_am
  * of destination block b (2^(total_bits-m) amplitudes) -- normally memory of a PEER GPU mapped
  * into this process (ua_ipc_open), so the tiles travel over NVLink while the pass computes.
  * num_gates may be 0 (pure scatter copy).  One state only (total_amps == 2^total_bits), shared
- * gates only.  The caller orders the pass against the peers' reads (a collective barrier).    */
+ * gates only.  The caller orders the pass against the peers' reads (a collective barrier).
+ * visit_xor: tiles whose scatter bits have the value v are visited when the kernel's tile
+ * counter reaches v ^ visit_xor.  With visit_xor = this rank's own block number every rank
+ * writes to a different peer at any moment (no incast on one GPU's NVLink ingress).           */
 #define UA_MAX_SCATTER_BITS 3
 int ua_apply_fused_pass_scatter(int dtype, const void *in, long long total_amps, int total_bits,
                                 int tile_low_bits, int num_high, const int *host_high_pos,
                                 int num_gates, const int *host_gate_k, const int *host_gate_bits,
                                 const long long *host_gate_offset, const void *gate_mats,
                                 int num_scatter_bits, const int *host_scatter_pos,
-                                void *const *host_dst_ptrs, void *stream);
+                                void *const *host_dst_ptrs, int visit_xor, void *stream);
 
 /* Peer memory for the scatter pass: export a device allocation of this process / map one of
  * another process on the same node (CUDA IPC).  ua_ipc_export writes a 64-byte handle for the

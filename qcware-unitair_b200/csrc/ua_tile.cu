@@ -66,6 +66,9 @@ struct FusedArgs {
     // output index; their values select one of 2^m destination buffers (peer GPUs' memory
     // mapped into this process).  tstart_out = tstart in the compressed index.
     int scatter_m;
+    unsigned long long tile_xor; // flips scatter bits of every tile's base: rank-dependent visiting order
+    int nins;                    // scatter pass: tile counter -> base inserts zeros at ins[] (tile high bits and
+    int ins[UA_MAX_TILE_BITS + UA_MAX_SCATTER_BITS];   // scatter bits, ascending); its low m bits are the scatter bits
     int vpos[UA_MAX_SCATTER_BITS];
     int tstart_out[6];
     void *dst[1 << UA_MAX_SCATTER_BITS];
@@ -532,8 +535,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
     auto tile_base = [&](long long tile_id, long long &row) -> uint64_t {
         row = tile_id / a.tiles_per_row;
         const long long j = tile_id - row * a.tiles_per_row;
-        uint64_t base = (uint64_t)j << a.L;
-        for (int i = 0; i < a.H; ++i) base = insert_zero(base, a.high[i]);
+        uint64_t base;
+        if (a.scatter_m > 0) {
+            // consecutive tiles go to different destinations (the low m bits of the counter are the
+            // scatter bits): every GPU writes to all its peers all the time, like a ring-less
+            // all-to-all, instead of one peer after the other (incast when ranks drift apart)
+            base = (uint64_t)(j >> a.scatter_m) << a.L;
+            for (int i = 0; i < a.nins; ++i) base = insert_zero(base, a.ins[i]);
+            for (int i = 0; i < a.scatter_m; ++i) base |= (uint64_t)((j >> i) & 1) << a.vpos[i];
+            base ^= a.tile_xor;      // a bijection on tiles (only scatter bits flip)
+        } else {
+            base = (uint64_t)j << a.L;
+            for (int i = 0; i < a.H; ++i) base = insert_zero(base, a.high[i]);
+        }
         return base + ((uint64_t)row << a.total_bits);
     };
     auto run_offset = [&](unsigned r) -> uint64_t {   // amplitude offset of run r inside a tile
@@ -1482,7 +1496,7 @@ extern "C" int ua_apply_fused_pass_scatter(int dtype, const void *in, long long 
                                            int num_gates, const int *host_gate_k, const int *host_gate_bits,
                                            const long long *host_gate_offset, const void *gate_mats,
                                            int num_scatter_bits, const int *host_scatter_pos,
-                                           void *const *host_dst_ptrs, void *stream) {
+                                           void *const *host_dst_ptrs, int visit_xor, void *stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const char *who = "ua_apply_fused_pass_scatter";
     if (num_scatter_bits < 1 || num_scatter_bits > UA_MAX_SCATTER_BITS || !host_scatter_pos || !host_dst_ptrs) {
@@ -1506,6 +1520,15 @@ extern "C" int ua_apply_fused_pass_scatter(int dtype, const void *in, long long 
         for (int i = 0; i < a.H; ++i)
             if (a.high[i] == v) { set_error("%s: scatter bit %d is a tile bit", who, v); return UA_ERR_INVALID; }
         a.vpos[j] = v;
+        if ((visit_xor >> j) & 1) a.tile_xor |= 1ull << v;
+    }
+    {   // merged ascending list of the tile's high bits and the scatter bits
+        int i = 0, j = 0;
+        a.nins = 0;
+        while (i < a.H || j < num_scatter_bits) {
+            if (j >= num_scatter_bits || (i < a.H && a.high[i] < a.vpos[j])) a.ins[a.nins++] = a.high[i++];
+            else a.ins[a.nins++] = a.vpos[j++];
+        }
     }
     if (a.T > total_bits - num_scatter_bits) { set_error("%s: tile larger than the destination blocks", who); return UA_ERR_INVALID; }
     for (int b = 0; b < (1 << num_scatter_bits); ++b) {

@@ -78,7 +78,7 @@ def _declare(L):
                                          p_int, c_void_p, c_void_p]
     L.ua_apply_fused_pass_scatter.argtypes = [c_int, c_void_p, c_longlong, c_int, c_int, c_int, p_int,
                                               c_int, p_int, p_int, p_ll, c_void_p, c_int, p_int,
-                                              POINTER(c_void_p), c_void_p]
+                                              POINTER(c_void_p), c_int, c_void_p]
     L.ua_ipc_export.argtypes = [c_void_p, c_void_p, p_ll]
     L.ua_ipc_open.argtypes = [c_void_p, c_longlong, POINTER(c_void_p)]
     L.ua_ipc_close.argtypes = [c_void_p, c_longlong]

@@ -488,11 +488,11 @@ class ScatterTail:
     def num_passes(self):
         return len(self.inplace_launches) + 1
 
-    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None):
+    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None, visit_xor: int = 0):
         """In-place passes on `state`, then the tail pass from `state` into the 2^m destination
         blocks `dst_ptrs` (device addresses, possibly of peer GPUs).  `before_scatter` is called
         right before the scatter pass is enqueued (cross-rank fence when the destinations may
-        still be in use)."""
+        still be in use).  visit_xor: see ua_apply_fused_pass_scatter (rank-dependent tile order)."""
         cc = self.compiled
         if self.inplace_launches:
             cc._run_launches(self.inplace_launches, state, state)
@@ -504,7 +504,7 @@ class ScatterTail:
             L.check(L.lib().ua_apply_fused_pass_scatter(
                 L.dtype_code(self.dtype), state.data_ptr(), 1 << self.n, self.n, pl.low, pl.nhigh, pl.high,
                 pl.ngates, pl.ks, pl.bits, pl.offs, cc.mats.data_ptr() if pl.ngates else None,
-                self.m, self.victims, L.ptr_array(list(dst_ptrs)), L.stream_ptr(dev)))
+                self.m, self.victims, L.ptr_array(list(dst_ptrs)), int(visit_xor), L.stream_ptr(dev)))
 
 
 class _AdjointCircuit(torch.autograd.Function):

@@ -227,7 +227,9 @@ class CudaEngine:
         a = exchange_block_id(st.rank, ep)
         spare_of = peers[st._spare().data_ptr()]
         dst = [spare_of[exchange_peer(st.rank, ep, b)] + a * block_bytes for b in range(1 << m)]
-        tail.run(st.local, dst, before_scatter=before_scatter)
+        # visit order rotated by this rank's own block number: at any moment every rank of the
+        # exchange group is writing to a different peer
+        tail.run(st.local, dst, before_scatter=before_scatter, visit_xor=a)
 
     def permute(self, src_bits, shard, out):
         from . import _lib as L

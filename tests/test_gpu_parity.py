@@ -759,7 +759,8 @@ def test_fused_pass_scatter_matches_permute_and_split(ua, dt, n, victims):
             assert tail.reused, "a last pass that avoids the victim bits must be reused"
         out = torch.full_like(st, float("nan"))
         work = st.clone()
-        tail.run(work, [out.data_ptr() + b * block_bytes for b in range(1 << m)])
+        tail.run(work, [out.data_ptr() + b * block_bytes for b in range(1 << m)],
+                 visit_xor=int(rng.integers(0, 1 << m)))
         torch.cuda.synchronize()
         want = _scatter_reference(ref, n, victims)
         if tail.reused:      # same gates, different tile shape: rounding may differ in the last pass
@@ -780,7 +781,7 @@ def test_fused_pass_scatter_rejects_bad_arguments(ua):
 
     def call(low, high, victims, total=1 << n):
         return lib.ua_apply_fused_pass_scatter(0, st.data_ptr(), total, n, low, len(high), L.int_array(high) if high else None,
-                                               0, None, None, None, None, len(victims), L.int_array(victims), dst, stream)
+                                               0, None, None, None, None, len(victims), L.int_array(victims), dst, 1, stream)
     assert call(7, [7, 8, 9, 10, 11, 12], [13]) == 0
     assert call(7, [7, 8, 9, 10, 11, 13], [13]) != 0        # scatter bit inside the tile
     assert call(7, [8, 9, 10], [3]) != 0                    # scatter bit among the low bits
