@@ -192,6 +192,21 @@ int ua_permute_bits(int dtype, void *out, const void *in, int num_bits, long lon
 int ua_apply_sign_masks(int dtype, void *out, const void *in, int num_qubits, long long batch,
                         int num_masks, const unsigned long long *host_masks, void *stream);
 
+/* Sampling in the computational basis (measure, src/unitair/simulation/measurement.py:9-70)
+ * without materialising abs_squared(state) or torch.distributions.Categorical's temporaries:
+ *   ua_sample_block_sums  out_f64[b] = sum of |in[i]|^2 over block b of 2^block_log2 amplitudes
+ *                         (one read of the state, fp64 accumulation);
+ *   ua_sample_locate      for every draw targets_f64[s] in [0, total) find the amplitude index i
+ *                         with cdf(i-1) <= draw < cdf(i), given the INCLUSIVE cumulative sum of
+ *                         the block sums (block_cdf_f64); out_index_i64[s] = i.
+ * 5 <= block_log2 <= 20.  The cumulative sum of the (few) block sums and the uniform draws are
+ * the caller's (tiny tensors).                                                                */
+int ua_sample_block_sums(int dtype, void *out_f64, const void *in, long long elems,
+                         int block_log2, void *stream);
+int ua_sample_locate(int dtype, void *out_index_i64, const void *in, long long elems,
+                     int block_log2, const void *block_cdf_f64, const void *targets_f64,
+                     long long num_samples, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -354,3 +354,22 @@ def apply_operator_grads(operator, qubits, state, grad_out):
         if a == 1 and b != 1:
             gu = gu.sum(axis=ax, keepdims=True)
     return gu, grad_state
+
+
+def measurement_probabilities(state):
+    """The distribution the reference samples from: Categorical(probs=abs_squared(state))
+    (src/unitair/simulation/measurement.py:41-42; Categorical normalises probs by their sum)."""
+    p = abs_squared(np.asarray(state)).astype(np.float64)
+    return p / p.sum()
+
+
+def sample_indices(state, uniforms):
+    """Inverse-CDF sampling from measurement_probabilities(state): draw u in [0, 1) selects the
+    first index whose cumulative probability exceeds u.  The reference draws from the same
+    distribution with torch's multinomial sampler (measurement.py:42-43), whose random stream
+    cannot be reproduced outside torch: parity for measure() is distributional."""
+    state = np.asarray(state)
+    p = (state.real.astype(np.float64) ** 2 + state.imag.astype(np.float64) ** 2)
+    cdf = np.cumsum(p)
+    t = np.asarray(uniforms, dtype=np.float64) * cdf[-1]
+    return np.minimum(np.searchsorted(cdf, t, side="right"), len(p) - 1)

@@ -82,13 +82,17 @@ def _declare(L):
     L.ua_ipc_export.argtypes = [c_void_p, c_void_p, p_ll]
     L.ua_ipc_open.argtypes = [c_void_p, c_longlong, POINTER(c_void_p)]
     L.ua_ipc_close.argtypes = [c_void_p, c_longlong]
+    L.ua_sample_block_sums.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p]
+    L.ua_sample_locate.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p,
+                                   c_longlong, c_void_p]
     L.ua_permute_bits.argtypes = [c_int, c_void_p, c_void_p, c_int, c_longlong, p_int, c_void_p]
     L.ua_apply_sign_masks.argtypes = [c_int, c_void_p, c_void_p, c_int, c_longlong, c_int,
                                       POINTER(c_ulonglong), c_void_p]
     for name in ("ua_apply_sign_masks", "ua_apply_gate", "ua_gate_grad", "ua_apply_phase", "ua_phase_backward",
                  "ua_abs_squared", "ua_norm_squared", "ua_diag_expectation", "ua_inner_product",
                  "ua_fused_limits", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits",
-                 "ua_apply_fused_pass_scatter", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close"):
+                 "ua_apply_fused_pass_scatter", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close",
+                 "ua_sample_block_sums", "ua_sample_locate"):
         getattr(L, name).restype = c_int
 
 

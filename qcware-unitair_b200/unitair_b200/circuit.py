@@ -109,15 +109,34 @@ def _sorted_to_gate_index(bits):
     return None if idx == list(range(1 << k)) else idx
 
 
+def plan_passes_tail_first(gate_bits: Sequence[Sequence[int]], geo: TileGeometry, forbidden_last,
+                           **kw) -> List[Pass]:
+    """Like plan_passes, but planned from the END of the list: the LAST pass is the greedy, full
+    one (leftover gates end up in the first passes) and none of its tile bits is in
+    `forbidden_last`.  Used for the passes in front of a global-qubit exchange: the last pass
+    then stores straight into the peers' memory (ScatterTail), and the more gates it holds the
+    more of the NVLink time they hide."""
+    n = len(gate_bits)
+    rev = [list(gate_bits[n - 1 - i]) for i in range(n)]
+    passes = plan_passes(rev, geo, forbidden_first=forbidden_last, **kw)
+    out = []
+    for p in reversed(passes):
+        out.append(Pass(high=p.high, gates=[n - 1 - g for g in reversed(p.gates)], direct=p.direct))
+    return out
+
+
 def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
                 max_gates: int = L.MAX_FUSED_GATES, max_mat_elems: int = 2048,
-                lookahead: int = 512, max_fused_k: int = MAX_FUSED_K) -> List[Pass]:
+                lookahead: int = 512, max_fused_k: int = MAX_FUSED_K,
+                forbidden_first=None) -> List[Pass]:
     """Cut an ordered gate list into passes.
 
     gate_bits[g] are the index-bit positions gate g acts on.  Gates are only reordered
     across gates they share no bit with (a skipped gate blocks its bits for the rest of
     the pass), so the product of the passes equals the original circuit.
+    forbidden_first: bit positions that must not be tile bits of the FIRST pass.
     """
+    forbidden = set(forbidden_first or ())
     n_gates = len(gate_bits)
     done = [False] * n_gates
     passes: List[Pass] = []
@@ -127,13 +146,14 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             first += 1
             continue
         k0 = len(gate_bits[first])
+        banned = forbidden if not passes else set()
         if k0 > max_fused_k:
             passes.append(Pass(high=[], gates=[first], direct=True))
             done[first] = True
             continue
         cur = Pass()
         high = set()
-        blocked = set()
+        blocked = set(banned)
         mat_elems = 0
         scanned = 0
         for g in range(first, n_gates):
@@ -158,17 +178,23 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             done[g] = True
             if len(blocked) >= geo.total_bits:
                 break
+        if not cur.gates:
+            # nothing fits under the ban (the first gate touches a forbidden bit): an empty first
+            # pass would loop forever -- lift the ban, the caller copes (extra copy pass)
+            forbidden = set()
+            passes.append(None)
+            continue
         # fill the unused high slots so the tile is full: first positions that keep the number
         # of TMA dimensions (extend an existing run), then anything
         while len(high) < geo.max_high:
-            free = [p for p in range(geo.low_bits, geo.total_bits) if p not in high]
+            free = [p for p in range(geo.low_bits, geo.total_bits) if p not in high and p not in banned]
             if not free:
                 break
             best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits), p))
             high.add(best)
         cur.high = sorted(high)
         passes.append(cur)
-    return passes
+    return [p for p in passes if p is not None]
 
 
 # --------------------------------------------------------------------------- #
@@ -326,7 +352,7 @@ class CompiledCircuit:
     """
 
     def __init__(self, gates, num_qubits: int, dtype: torch.dtype, batch_shape=(),
-                 geometry: TileGeometry = None, merge: bool = True):
+                 geometry: TileGeometry = None, merge: bool = True, tail_forbidden=None):
         from . import states
         n = num_qubits
         self.n = n
@@ -352,7 +378,14 @@ class CompiledCircuit:
                 self.gates = merge_gates(self.gates)
         self.geo = geometry or default_geometry(n, dtype)
         self.gate_bits = [[n - 1 - q for q in qs] for qs, _ in self.gates]
-        self.passes = plan_passes(self.gate_bits, self.geo) if self.gates else []
+        if not self.gates:
+            self.passes = []
+        elif tail_forbidden:
+            # index bits that leave the shard right after this circuit (sharded.py): plan from
+            # the end so that the last pass is full and avoids them
+            self.passes = plan_passes_tail_first(self.gate_bits, self.geo, list(tail_forbidden))
+        else:
+            self.passes = plan_passes(self.gate_bits, self.geo)
         if self.gates:
             self.mats, self.offsets, self.row_stride = _pack_gates([m for _, m in self.gates],
                                                                   self.batch_shape)

@@ -193,9 +193,11 @@ class CudaEngine:
     def __init__(self, dtype):
         self.dtype = dtype
 
-    def compile(self, gates_local, n_local):
+    def compile(self, gates_local, n_local, tail_victims=None):
         from . import circuit
-        return circuit.CompiledCircuit(gates_local, n_local, self.dtype) if gates_local else None
+        if not gates_local:
+            return None
+        return circuit.CompiledCircuit(gates_local, n_local, self.dtype, tail_forbidden=tail_victims)
 
     def run(self, compiled, shard):
         if compiled is not None:
@@ -406,18 +408,23 @@ class ShardedCircuit:
                                                    self.start_layout, restore=restore,
                                                    min_victim_bit=min_victim)
         nl = self.n_local
-        self.compiled = []
-        for ep in self.epochs:
-            local_gates = [([nl - 1 - p for p in bits], self.gates[gi][1])
-                           for gi, bits in zip(ep.gates, ep.local_bits)]
-            self.compiled.append(self.engine.compile(local_gates, nl))
         # scatter tails: epoch i ends with the exchange that opens epoch i+1
-        self.tails = [None] * len(self.epochs)
+        want_tail = [False] * len(self.epochs)
         if self.p2p:
             for i in range(len(self.epochs) - 1):
                 nxt = self.epochs[i + 1]
-                if nxt.incoming and min(nxt.victim_bits) >= min_victim:
-                    self.tails[i] = self.engine.scatter_tail(self.compiled[i], nl, nxt.victim_bits)
+                want_tail[i] = bool(nxt.incoming) and min(nxt.victim_bits) >= min_victim
+        self.compiled = []
+        self.tails = [None] * len(self.epochs)
+        for i, ep in enumerate(self.epochs):
+            local_gates = [([nl - 1 - p for p in bits], self.gates[gi][1])
+                           for gi, bits in zip(ep.gates, ep.local_bits)]
+            if want_tail[i]:
+                victims = self.epochs[i + 1].victim_bits
+                self.compiled.append(self.engine.compile(local_gates, nl, tail_victims=victims))
+                self.tails[i] = self.engine.scatter_tail(self.compiled[i], nl, victims)
+            else:
+                self.compiled.append(self.engine.compile(local_gates, nl))
         self.num_swaps = sum(1 for ep in self.epochs if ep.incoming)
         self.num_fused_swaps = sum(1 for t in self.tails if t is not None)
         self.num_passes = 0

@@ -6,3 +6,4 @@ from .operations import swap, roll_qubits, permute_qubits
 from .operations import act_first_qubits
 from .operations import multi_cz
 from .operations import multi_controlled_x, multi_controlled_z
+from .measurement import measure, MeasurementHistogram

@@ -788,3 +788,58 @@ def test_fused_pass_scatter_rejects_bad_arguments(ua):
     assert call(7, [7, 8, 9, 10, 11, 12, 13], [6]) != 0
     assert call(7, [7, 8], [13], total=2 << n) != 0         # one state only
     torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------- measure
+@pytest.mark.parametrize("dt", ["c64", "c128"])
+@pytest.mark.parametrize("n", [3, 11, 12, 17, 20])
+def test_sample_indices_match_oracle_inverse_cdf(ua, dt, n):
+    from unitair_b200.simulation import measurement
+    rng = np.random.default_rng(n)
+    st = rnd_c(rng, (2 ** n,), dt, scale=0.7)        # not normalised: the sampler normalises
+    if n == 17:
+        st[: 2 ** 16] = 0                            # empty blocks in front
+    u = rng.random(4096)
+    u[:3] = [0.0, 0.5, 1.0 - 2 ** -53]
+    got = host(measurement.sample_indices(dev(st), len(u), uniforms=torch.from_numpy(u)))
+    want = orc.sample_indices(st, u)
+    # identical except for draws that land within rounding of a CDF step (different fp64
+    # summation order): those may move to a neighbouring index with non-zero probability
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) <= 2, (len(bad), got[bad][:5], want[bad][:5])
+    p = np.abs(st.astype(np.complex128)) ** 2
+    cdf = np.cumsum(p)
+    for i in bad:
+        t = u[i] * cdf[-1]
+        assert abs(cdf[min(got[i], want[i])] - t) < 1e-9 * cdf[-1]
+    assert np.all(p[got] > 0)
+
+
+def test_measure_histogram(ua):
+    rng = np.random.default_rng(3)
+    n = 10
+    st = rnd_state(rng, n, (), "c64")
+    torch.manual_seed(5)
+    num = 400000
+    raw = ua.simulation.measure(dev(st), num, raw_output=True)
+    assert sum(raw.values()) == num and all(isinstance(k, int) for k in raw)
+    p = orc.measurement_probabilities(st)
+    counts = np.zeros(2 ** n)
+    for k, c in raw.items():
+        counts[k] = c
+    chi2 = np.sum((counts - num * p) ** 2 / (num * p))
+    assert chi2 < 2 ** n + 6 * math.sqrt(2 * 2 ** n), chi2
+    hist = ua.simulation.measure(dev(st), 5000)
+    assert isinstance(hist, ua.simulation.MeasurementHistogram) and hist.num_qubits == n
+    cs = list(hist.histogram.values())
+    assert cs == sorted(cs, reverse=True) and sum(cs) == 5000
+    assert all(len(k) == n and set(k) <= {"0", "1"} for k in hist.histogram)
+    assert hist["0" * n] >= 0
+    with pytest.raises(KeyError):
+        hist["012"]
+    # README Bell state: only |00> and |11> are ever observed
+    bell = torch.tensor([2 ** -0.5, 0, 0, 2 ** -0.5], dtype=torch.complex64, device="cuda")
+    hb = ua.simulation.measure(bell, 1000)
+    assert hb.observed_samples <= {"00", "11"} and hb["00"] + hb["11"] == 1000
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.simulation.measure(torch.zeros(4, dtype=torch.complex64), 3)

@@ -136,3 +136,25 @@ def test_oracle_errors():
         orc.apply_operator(np.zeros((3, 3), np.complex64), (0,), st)
     with pytest.raises(ValueError):
         orc.apply_all_qubits(np.eye(4, dtype=np.complex64), st)
+
+
+def test_oracle_sampling_distribution_matches_reference_probabilities():
+    """measure(): the oracle's inverse CDF samples the distribution the reference hands to
+    torch.distributions.Categorical (abs_squared, normalised), measurement.py:41-42."""
+    rng = np.random.default_rng(12)
+    n = 6
+    st = (rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)).astype(np.complex64) * 0.3
+    p = orc.measurement_probabilities(st)
+    assert abs(p.sum() - 1.0) < 1e-12
+    assert np.allclose(p * np.sum(np.abs(st.astype(np.complex128)) ** 2), np.abs(st.astype(np.complex128)) ** 2, rtol=1e-6)
+    u = rng.random(200000)
+    idx = orc.sample_indices(st, u)
+    counts = np.bincount(idx, minlength=2 ** n)
+    chi2 = np.sum((counts - len(u) * p) ** 2 / (len(u) * p))
+    assert chi2 < 2 ** n + 6 * np.sqrt(2 * 2 ** n), chi2          # mean 63, sigma ~11
+    # deterministic corner cases: a basis state, and u = 0 / u -> 1
+    e3 = np.zeros(8, dtype=np.complex64)
+    e3[3] = 1
+    assert set(orc.sample_indices(e3, rng.random(50)).tolist()) == {3}
+    assert orc.sample_indices(st, [0.0])[0] == 0
+    assert orc.sample_indices(st, [1.0 - 1e-16])[0] == 2 ** n - 1

@@ -17,7 +17,7 @@ from unitair_b200 import sharded
 class OracleEngine:
     """Test-only local engine: applies gates / bit permutations to a CPU shard with the oracle."""
 
-    def compile(self, gates_local, n_local):
+    def compile(self, gates_local, n_local, tail_victims=None):
         return [(qs, m.numpy()) for qs, m in gates_local]
 
     def num_passes(self, compiled):
