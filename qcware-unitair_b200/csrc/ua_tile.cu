@@ -504,7 +504,7 @@ __device__ __forceinline__ void apply_any_gate(typename VecOf<R>::type *tv,
 
 // Persistent kernel: CTA b processes tiles b, b + gridDim.x, ...  Shared memory layout:
 // [nstage tile buffers][gate matrices]; mbarriers are static.
-template <typename R, int FUSED_THREADS, int MINB>
+template <typename R, int FUSED_THREADS, int MINB, bool SCATTER = false>
 __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const __grid_constant__ FusedArgs a) {
     constexpr bool LEAN = (FUSED_THREADS * MINB > 512);
     using C = typename CplxOf<R>::type;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
         row = tile_id / a.tiles_per_row;
         const long long j = tile_id - row * a.tiles_per_row;
         uint64_t base;
-        if (a.scatter_m > 0) {
+        if constexpr (SCATTER) {
             // consecutive tiles go to different destinations (the low m bits of the counter are the
             // scatter bits): every GPU writes to all its peers all the time, like a ring-less
             // all-to-all, instead of one peer after the other (incast when ranks drift apart)
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, MINB) fused_pass_kernel(const _
         long long row;
         const uint64_t base = tile_base(tile_id, row);
         const unsigned src = smem_u32(smem_raw + (size_t)s * tile_bytes);
-        if (a.scatter_m > 0) {
+        if constexpr (SCATTER) {
             // the tile goes to ONE destination buffer (no scatter bit is a tile bit), at the
             // position its index has once the scatter bits are squeezed out
             unsigned b = 0;
@@ -1255,10 +1255,10 @@ static int env_int(const char *name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
-template <typename R, int FUSED_THREADS, int MINB = 512 / FUSED_THREADS>
+template <typename R, int FUSED_THREADS, int MINB = 512 / FUSED_THREADS, bool SCATTER = false>
 static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaStream_t st) {
     static bool attr_set = false;
-    auto kern = fused_pass_kernel<R, FUSED_THREADS, MINB>;
+    auto kern = fused_pass_kernel<R, FUSED_THREADS, MINB, SCATTER>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { set_error("ua_apply_fused_pass: cannot raise shared memory limit: %s", cudaGetErrorString(e)); return UA_ERR_CUDA; }
@@ -1540,6 +1540,6 @@ extern "C" int ua_apply_fused_pass_scatter(int dtype, const void *in, long long 
     const size_t csize = (dtype == UA_C64) ? 8 : 16;
     const size_t tile_bytes = ((size_t)1 << a.T) * csize;
     const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
-    if (dtype == UA_C64) return launch_fused<float, 256, 3>(a, tile_bytes, mat_bytes, st);
-    return launch_fused<double, 128>(a, tile_bytes, mat_bytes, st);
+    if (dtype == UA_C64) return launch_fused<float, 256, 3, true>(a, tile_bytes, mat_bytes, st);
+    return launch_fused<double, 128, 4, true>(a, tile_bytes, mat_bytes, st);
 }
