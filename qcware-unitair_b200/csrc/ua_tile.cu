@@ -1282,7 +1282,10 @@ static int launch_fused(FusedArgs &a, size_t tile_bytes, size_t mat_bytes, cudaS
     a.nstage = nstage;
     a.swizzle = env_int("UA_FUSED_SWZ", 0);
     a.use_f2 = env_int("UA_FUSED_F2", 0);
-    a.l2_prefetch = env_int("UA_FUSED_L2PF", nstage <= 2 ? 1 : 0);
+    // L2 prefetch of the tile after next: measured neutral on time (147.9 vs 148.3 ms per bench step)
+    // but 15-20 % of the prefetched lines are evicted before use and read from HBM twice
+    // (ncu: dram read 9.7-10.3 GB per pass instead of 8.59 GB), so it is off by default
+    a.l2_prefetch = env_int("UA_FUSED_L2PF", 0);
     a.stagger_ns = env_int("UA_FUSED_STAGGER_NS", 0);
     a.trace = g_trace_ptr;
     a.num_sms = sms;
