@@ -13,6 +13,8 @@ from . import simulation
 from . import gates
 from . import initializations
 from . import circuit
+from . import hoststream
+from .hoststream import HostCircuitStream
 
 from .states.shapes import StateLayout
 from .initializations import unit_vector, uniform_superposition, rand_state

@@ -843,3 +843,37 @@ def test_measure_histogram(ua):
     assert hb.observed_samples <= {"00", "11"} and hb["00"] + hb["11"] == 1000
     with pytest.raises(RuntimeError, match="CUDA"):
         ua.simulation.measure(torch.zeros(4, dtype=torch.complex64), 3)
+
+
+# --------------------------------------------------------------------------- host pipeline
+def test_host_circuit_stream_matches_apply_gates(ua):
+    """HostCircuitStream: jobs whose upload, circuit and download overlap on three streams must
+    deliver exactly what circuit.apply_gates gives for each job on its own."""
+    n = 18
+    rng = np.random.default_rng(21)
+    jobs = []
+    for j in range(7):
+        st = torch.from_numpy(rnd_state(rng, n, (), "c64")).pin_memory()
+        gl = []
+        for _ in range(12):
+            a, b = rng.choice(n, 2, replace=False)
+            gl.append(([int(a), int(b)], torch.from_numpy(haar(rng, 4, "c64")).pin_memory()))
+            gl.append(([int(rng.integers(n))], torch.from_numpy(haar(rng, 2, "c64")).pin_memory()))
+        jobs.append((gl, st, torch.empty(2 ** n, dtype=torch.complex64).pin_memory()))
+    hs = ua.HostCircuitStream(n, torch.complex64, "cuda", depth=3)
+    for gl, h_in, h_out in jobs:
+        hs.submit(gl, h_in, h_out)
+    hs.drain()
+    for gl, h_in, h_out in jobs:
+        ref = ua.circuit.apply_gates([(qs, u.cuda()) for qs, u in gl], h_in.cuda())
+        assert torch.equal(torch.view_as_real(h_out), torch.view_as_real(ref.cpu()))
+    # a compiled plan can be reused, and a second round after drain() works
+    cc = None
+    outs = [torch.empty(2 ** n, dtype=torch.complex64).pin_memory() for _ in range(4)]
+    for o in outs:
+        cc = hs.submit(jobs[0][0], jobs[0][1], o, compiled=cc)
+    hs.drain()
+    for o in outs:
+        assert torch.equal(torch.view_as_real(o), torch.view_as_real(jobs[0][2]))
+    with pytest.raises(RuntimeError):
+        ua.HostCircuitStream(n, torch.complex64, "cpu")
