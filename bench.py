@@ -432,7 +432,7 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 return e0.elapsed_time(e1) / 1e3
             run_jobs(1, True)
-            k_e2e = max(3, min(args.steps, 6))
+            k_e2e = max(8, args.steps)
             t_serial = run_jobs(2, True) / 2
             t_e2e = run_jobs(k_e2e, False)
             line["e2e"] = {"value": updates_per_step * k_e2e / t_e2e, "unit": UNIT,
