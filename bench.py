@@ -267,11 +267,28 @@ def run_ours(args):
         # (no swap-back at the end of a step), so each step has its own pre-built plan, exactly
         # as the single-GPU arm pre-compiles its circuit outside the timed region.
         n_plans = max(args.warmup, 3) + args.steps
-        plans, layout = [], sharded.identity_layout(n_total)
-        for _ in range(n_plans):
-            pl_ = sharded.ShardedCircuit(gates_dev, n_total, torch.complex64, world, layout=layout, restore=False)
-            plans.append(pl_)
-            layout = pl_.end_layout
+
+        def build_plans(exchange):
+            out_, layout = [], sharded.identity_layout(n_total)
+            for _ in range(n_plans):
+                pl_ = sharded.ShardedCircuit(gates_dev, n_total, torch.complex64, world, layout=layout,
+                                             restore=False, exchange=exchange)
+                out_.append(pl_)
+                layout = pl_.end_layout
+            return out_
+        exchange_mode = None
+        plans = build_plans(exchange_mode)
+        if plans[0].p2p:
+            # peer mapping (CUDA IPC) is set up collectively on first use: if this box refuses it,
+            # every rank fails the same way and falls back to the send/recv exchange -- loudly
+            try:
+                sstate.peer_pointers()
+            except Exception as e:  # pragma: no cover
+                if rank == 0:
+                    print(f"bench: peer-memory mapping failed ({e!r}); using the NCCL send/recv exchange",
+                          file=sys.stderr, flush=True)
+                exchange_mode = "nccl"
+                plans = build_plans(exchange_mode)
         plan_iter = iter(plans)
         step = lambda: next(plan_iter).run(sstate)   # noqa: E731
         timed = plans[max(args.warmup, 3):max(args.warmup, 3) + args.steps]
@@ -346,7 +363,8 @@ def run_ours(args):
                 d_gates = [(qs, u.to(dev, non_blocking=True)) for qs, u in h_gates]
                 sstate.local.copy_(h_in, non_blocking=True)
                 sstate.layout = sharded.identity_layout(n_total)
-                sc = sharded.ShardedCircuit(d_gates, n_total, torch.complex64, world, restore=False)
+                sc = sharded.ShardedCircuit(d_gates, n_total, torch.complex64, world, restore=False,
+                                            exchange=exchange_mode)
                 sc.run(sstate)
                 h_out.copy_(sstate.local, non_blocking=True)
             e2e_step()
@@ -372,7 +390,8 @@ def run_ours(args):
     if world > 1:
         # untimed extra step with per-phase device timing (permute / exchange / gates), rank 0
         tm = {}
-        tplan = sharded.ShardedCircuit(gates_dev, n_total, torch.complex64, world, layout=sstate.layout, restore=False)
+        tplan = sharded.ShardedCircuit(gates_dev, n_total, torch.complex64, world, layout=sstate.layout,
+                                       restore=False, exchange=exchange_mode)
         tplan.run(sstate, timing=tm)
         line["phase_ms_per_step_rank0"] = {k: round(v, 2) for k, v in tm.items()}
         if tm.get("exchange") and not tplan.p2p:
