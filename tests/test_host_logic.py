@@ -164,3 +164,24 @@ def test_tail_first_planner_preserves_the_circuit_and_avoids_forbidden_bits():
             ref = orc.apply_operator(u, qs, ref)
         got = _apply_plan_with_oracle(gates, state, passes)
         assert np.linalg.norm(got - ref) <= 1e-10 * np.linalg.norm(ref)
+
+
+def test_scatter_tail_copy_pass_geometry():
+    """Planning of the pass that scatters a shard to the peers (no CUDA needed for the plan):
+    the tile never contains a leaving bit, is full, and keeps the low bits together."""
+    for n, victims, dtype in [(30, [10, 19, 28], torch.complex64), (30, [27, 28, 29], torch.complex64),
+                              (33, [7], torch.complex64), (20, [12, 13], torch.complex128), (12, [10, 11], torch.complex64)]:
+        tail = circuit.ScatterTail(None, n, dtype, victims)
+        base = circuit.default_geometry(n, dtype)
+        tile = min(base.tile_bits, n - len(victims))
+        low = min(base.low_bits, tile)
+        assert not tail.reused and tail.num_passes == 1 and tail.launch.ngates == 0
+        high = list(tail.launch.high) if tail.launch.high is not None else []
+        assert tail.launch.low + len(high) == tile and tail.launch.low == tile - len(high)
+        assert len(high) == tile - low
+        assert not (set(high) & set(victims)) and all(low <= b < n for b in high)
+        assert high == sorted(high)
+    with pytest.raises(ValueError):
+        circuit.ScatterTail(None, 30, torch.complex64, [3])          # a leaving bit among the low bits
+    assert circuit._fill_high({9}, circuit.TileGeometry(10, 8, 7, 1), forbidden=[]) == [9]
+    assert circuit._fill_high(set(), circuit.TileGeometry(9, 9, 7, 2), forbidden=[8]) is None
