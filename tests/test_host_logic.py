@@ -40,6 +40,12 @@ def test_no_cpu_fallback():
         ua.abs_squared(st)
     with pytest.raises(RuntimeError, match="CUDA"):
         ua.diag_expectation_value(torch.zeros(8), st)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.simulation.measure(st, 10)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.HostCircuitStream(3, torch.complex64, "cpu")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ua.circuit.apply_gates([([0], op)], st)
 
 
 def test_validation_matches_reference_error_types():
