@@ -378,8 +378,9 @@ class ShardedState:
 
 
 class ShardedCircuit:
-    """A gate list planned once for a state sharded over `world` ranks and replayable
-    (the plan ends in the layout it started from)."""
+    """A gate list planned once for a state sharded over `world` ranks.  With restore=True the
+    plan ends in the qubit layout it started from and can be replayed; with restore=False it ends
+    in `end_layout` (pass that as `layout=` to the next circuit)."""
 
     def __init__(self, gates, num_qubits: int, dtype, world: int, engine=None,
                  layout: Optional[List[int]] = None, restore: bool = True, exchange: Optional[str] = None):
@@ -421,10 +422,16 @@ class ShardedCircuit:
                            for gi, bits in zip(ep.gates, ep.local_bits)]
             if want_tail[i]:
                 victims = self.epochs[i + 1].victim_bits
-                self.compiled.append(self.engine.compile(local_gates, nl, tail_victims=victims))
-                self.tails[i] = self.engine.scatter_tail(self.compiled[i], nl, victims)
-            else:
-                self.compiled.append(self.engine.compile(local_gates, nl))
+                try:
+                    comp = self.engine.compile(local_gates, nl, tail_victims=victims)
+                    self.tails[i] = self.engine.scatter_tail(comp, nl, victims)
+                    self.compiled.append(comp)
+                    continue
+                except ValueError:
+                    # no tile avoids the leaving bits (tiny shards): this exchange uses the
+                    # permute + send/recv formulation, which the epoch describes as well
+                    self.tails[i] = None
+            self.compiled.append(self.engine.compile(local_gates, nl))
         self.num_swaps = sum(1 for ep in self.epochs if ep.incoming)
         self.num_fused_swaps = sum(1 for t in self.tails if t is not None)
         self.num_passes = 0
