@@ -157,7 +157,7 @@ def test_sharded_circuit_matches_oracle(tmp_path, world, n, restore):
     assert int(swaps) >= 1
 
 
-@pytest.mark.parametrize("world,n,restore", [(2, 7, True), (4, 8, True), (4, 9, False)])
+@pytest.mark.parametrize("world,n,restore", [(2, 7, True), (4, 8, True), (4, 9, False), (8, 9, False)])
 def test_sharded_circuit_scatter_exchange_matches_oracle(tmp_path, world, n, restore):
     """The fused-scatter control flow (exchange delivered by the previous epoch's last pass into
     the peers' spare buffers, fence, buffer flip; send/recv fallback for restore exchanges that
