@@ -124,9 +124,17 @@ def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
         incoming = globals_needed[:g]
         # Belady: evict the local qubits whose next use is farthest away
         never = len(remaining) + 1
-        local_qubits = [q for q in range(n) if min_victim_bit <= phys[q] < n_local]
+        # never evict the partners of an incoming qubit in the gate that needs it first (the gate
+        # would stay non-local); among the rest prefer bits >= min_victim_bit, then anything
+        needed_now = set()
+        for q in incoming:
+            needed_now.update(gate_qubits[remaining[first_use[q]]])
+        all_local = [q for q in range(n) if phys[q] < n_local]
+        local_qubits = [q for q in all_local if phys[q] >= min_victim_bit and q not in needed_now]
         if len(local_qubits) < len(incoming):
-            local_qubits = [q for q in range(n) if phys[q] < n_local]
+            local_qubits = [q for q in all_local if q not in needed_now]
+        if len(local_qubits) < len(incoming):
+            local_qubits = all_local
         local_qubits.sort(key=lambda q: (-first_use.get(q, never), -phys[q]))
         victims = local_qubits[:len(incoming)]
         victims.sort(key=lambda q: phys[q])

@@ -1,0 +1,96 @@
+"""Hypothesis property tests (CPU) of the host-side planners: whatever the gate list, merging
+and pass / epoch planning must leave the circuit's product unchanged.  Checked with the numpy
+oracle on small states; modelled on the reference's own property-test style
+(tests/hypothesis_strategies/, tests/test_operations.py)."""
+import numpy as np
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import unitair_oracle as orc
+from unitair_b200 import circuit, sharded
+
+SETTINGS = dict(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+
+
+@st.composite
+def gate_lists(draw, max_qubits=7, max_gates=24, max_k=3):
+    n = draw(st.integers(3, max_qubits))
+    count = draw(st.integers(1, max_gates))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    gates = []
+    for _ in range(count):
+        k = int(rng.integers(1, min(max_k, n) + 1))
+        qs = rng.choice(n, k, replace=False).tolist()
+        u = rng.standard_normal((2 ** k, 2 ** k)) + 1j * rng.standard_normal((2 ** k, 2 ** k))
+        gates.append((qs, (u / np.linalg.norm(u, 2)).astype(np.complex128)))
+    state = rng.standard_normal(2 ** n) + 1j * rng.standard_normal(2 ** n)
+    return n, gates, state / np.linalg.norm(state)
+
+
+def _run(gates, state):
+    psi = state
+    for qs, u in gates:
+        psi = orc.apply_operator(np.asarray(u), list(qs), psi)
+    return psi
+
+
+def _close(a, b):
+    return np.linalg.norm(a - b) <= 1e-10 * max(1.0, np.linalg.norm(b))
+
+
+@settings(**SETTINGS)
+@given(gate_lists(), st.sampled_from([2, 3]))
+def test_merge_gates_preserves_the_product(case, max_k):
+    n, gates, state = case
+    merged = circuit.merge_gates([(qs, torch.from_numpy(u)) for qs, u in gates], max_k)
+    assert all(len(qs) <= max(max_k, 3) for qs, _ in merged)
+    assert len(merged) <= len(gates)
+    assert _close(_run([(qs, u.numpy()) for qs, u in merged], state), _run(gates, state))
+
+
+@settings(**SETTINGS)
+@given(gate_lists(max_qubits=8), st.integers(0, 3), st.booleans())
+def test_pass_planners_preserve_the_product(case, low, tail_first):
+    n, gates, state = case
+    tile = min(n, low + 3)
+    geo = circuit.TileGeometry(n, tile, min(low, tile), tile - min(low, tile))
+    bits = [[n - 1 - q for q in qs] for qs, _ in gates]
+    forbidden = [n - 1] if (tail_first and geo.low_bits < n - 1 and tile < n) else []
+    if tail_first and forbidden:
+        passes = circuit.plan_passes_tail_first(bits, geo, forbidden, max_gates=7)
+    else:
+        passes = circuit.plan_passes(bits, geo, max_gates=7)
+    assert sorted(g for p in passes for g in p.gates) == list(range(len(gates)))
+    for p in passes:
+        if p.direct:
+            continue
+        tile_bits = set(range(geo.low_bits)) | set(p.high)
+        assert len(p.gates) <= 7 and all(set(bits[g]) <= tile_bits for g in p.gates)
+    ordered = [gates[g] for p in passes for g in p.gates]
+    assert _close(_run(ordered, state), _run(gates, state))
+
+
+@settings(**SETTINGS)
+@given(gate_lists(max_qubits=8, max_k=2), st.integers(1, 2), st.integers(0, 3), st.booleans())
+def test_epoch_planner_respects_dependencies_and_locality(case, g, min_victim, restore):
+    n, gates, _ = case
+    g = min(g, n - 2)
+    gq = [qs for qs, _ in gates]
+    epochs, end = sharded.plan_epochs(gq, n, g, restore=restore, min_victim_bit=min_victim)
+    order = [gi for e in epochs for gi in e.gates]
+    assert sorted(order) == list(range(len(gq)))
+    pos = {gi: i for i, gi in enumerate(order)}
+    last = {}
+    for gi, qs in enumerate(gq):
+        for q in qs:
+            if q in last:
+                assert pos[last[q]] < pos[gi]
+            last[q] = gi
+    for e in epochs:
+        assert len(e.incoming) == len(e.victims) == len(e.rank_bits) == len(e.victim_bits) <= g
+        assert e.victim_bits == sorted(e.victim_bits)
+        for b in e.local_bits:
+            assert all(0 <= x < n - g for x in b)
+    if restore:
+        assert end == sharded.identity_layout(n)
