@@ -121,7 +121,18 @@ def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
             for q in gate_qubits[gi]:
                 first_use.setdefault(q, pos)
         globals_needed = sorted((q for q in first_use if phys[q] >= n_local), key=lambda q: first_use[q])
-        incoming = globals_needed[:g]
+        # bring in as many pending global qubits as there are local qubits that may leave: the
+        # partners of an incoming qubit in the gate that needs it first must stay
+        all_local = [q for q in range(n) if phys[q] < n_local]
+        take = min(g, len(globals_needed))
+        while take > 1:
+            partners = set()
+            for q in globals_needed[:take]:
+                partners.update(gate_qubits[remaining[first_use[q]]])
+            if sum(1 for q in all_local if q not in partners) >= take:
+                break
+            take -= 1
+        incoming = globals_needed[:take]
         # Belady: evict the local qubits whose next use is farthest away
         never = len(remaining) + 1
         # never evict the partners of an incoming qubit in the gate that needs it first (the gate
@@ -129,7 +140,6 @@ def plan_epochs(gate_qubits: Sequence[Sequence[int]], n: int, g: int,
         needed_now = set()
         for q in incoming:
             needed_now.update(gate_qubits[remaining[first_use[q]]])
-        all_local = [q for q in range(n) if phys[q] < n_local]
         local_qubits = [q for q in all_local if phys[q] >= min_victim_bit and q not in needed_now]
         if len(local_qubits) < len(incoming):
             local_qubits = [q for q in all_local if q not in needed_now]

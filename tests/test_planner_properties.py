@@ -94,3 +94,76 @@ def test_epoch_planner_respects_dependencies_and_locality(case, g, min_victim, r
             assert all(0 <= x < n - g for x in b)
     if restore:
         assert end == sharded.identity_layout(n)
+
+
+# ------------------------------------------------------------------------------------------
+# The epoch plan as data: simulate it on the FULL state in one process (physical index =
+# rank bits on top of the local bits) in both exchange formulations and compare with the
+# circuit itself.  Pins the meaning of Epoch.perm_src / rank_bits / victim_bits / local_bits.
+def _permute_local_bits(full, n, n_local, src):
+    """out bit p takes in bit src[p] (local bits only) -- ua_permute_bits semantics."""
+    t = full.reshape((2,) * n)                       # axis i <-> physical bit n-1-i
+    axes = list(range(n))
+    for p, s_ in enumerate(src):
+        axes[n - 1 - p] = n - 1 - s_
+    return np.transpose(t, axes).reshape(-1)
+
+
+def _exchange_bits(full, n, n_local, rank_bits):
+    """swap rank bit rank_bits[j] with local bit n_local - m + j (the block exchange)."""
+    m = len(rank_bits)
+    t = full.reshape((2,) * n)
+    axes = list(range(n))
+    for j, rb in enumerate(rank_bits):
+        a, b = n - 1 - (n_local + rb), n - 1 - (n_local - m + j)
+        axes[a], axes[b] = axes[b], axes[a]
+    return np.transpose(t, axes).reshape(-1)
+
+
+def _scatter(full, n, n_local, ep):
+    """The fused formulation: amplitude (rank, i) goes to rank' = rank with the swapped rank bits
+    replaced by the victim-bit values of i, position (own swapped rank bits) * 2^(nl-m) +
+    (i with the victim bits squeezed out)  (ua_apply_fused_pass_scatter + CudaEngine.run_scatter)."""
+    m = len(ep.incoming)
+    out = np.empty_like(full)
+    for rank in range(1 << (n - n_local)):
+        a = sharded.exchange_block_id(rank, ep)
+        for i in range(1 << n_local):
+            b = 0
+            for j, v in enumerate(ep.victim_bits):
+                b |= ((i >> v) & 1) << j
+            off = i
+            for v in sorted(ep.victim_bits, reverse=True):
+                off = ((off >> (v + 1)) << v) | (off & ((1 << v) - 1))
+            peer = sharded.exchange_peer(rank, ep, b)
+            out[(peer << n_local) | (a << (n_local - m)) | off] = full[(rank << n_local) | i]
+    return out
+
+
+def _simulate_plan(epochs, end_layout, gates, n, g, state, fused):
+    n_local = n - g
+    full = np.array(state)                             # identity layout: physical == logical
+    for ep in epochs:
+        if ep.incoming and fused:
+            full = _scatter(full, n, n_local, ep)
+        else:
+            if ep.perm_src is not None:
+                full = _permute_local_bits(full, n, n_local, ep.perm_src)
+            if ep.incoming:
+                full = _exchange_bits(full, n, n_local, ep.rank_bits)
+        for gi, bits in zip(ep.gates, ep.local_bits):
+            full = orc.apply_operator(gates[gi][1], [n - 1 - p for p in bits], full)
+    t = full.reshape((2,) * n)
+    axes = [n - 1 - end_layout[q] for q in range(n)]   # logical qubit q sits on physical bit layout[q]
+    return np.transpose(t, axes).reshape(-1)
+
+
+@settings(**SETTINGS)
+@given(gate_lists(max_qubits=7, max_k=2, max_gates=18), st.integers(1, 2), st.integers(0, 2), st.booleans(),
+       st.booleans())
+def test_epoch_plan_reproduces_the_circuit_in_both_exchange_formulations(case, g, min_victim, restore, fused):
+    n, gates, state = case
+    g = min(g, n - 2)
+    epochs, end = sharded.plan_epochs([qs for qs, _ in gates], n, g, restore=restore, min_victim_bit=min_victim)
+    got = _simulate_plan(epochs, end, gates, n, g, state, fused)
+    assert _close(got, _run(gates, state))
