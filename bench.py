@@ -193,7 +193,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "c64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": base,
@@ -339,7 +339,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": elapsed / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "c64",
         "data": "synthetic", "config": workload_config(args, world), "roofline": roofline,
         "gpu_launches": int(launches), "clocks": clocks,
     }
@@ -491,6 +491,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--qubits", type=int, default=int(os.environ.get("UA_BENCH_QUBITS", 30)),
                     help="qubits per GPU (the state has qubits + log2(gpus) qubits)")
+    ap.add_argument("--total-qubits", type=int, default=None,
+                    help="strong scaling: fixed state size, qubits per GPU = total - log2(gpus) "
+                         "(BASELINE config 5: 33 qubits on 1/2/4/8 GPUs)")
     ap.add_argument("--layers", type=int, default=10)
     ap.add_argument("--seed", type=int, default=202)
     ap.add_argument("--cpu-qubits", type=int, default=24,
@@ -498,6 +501,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    args.scaling = "weak"
+    if args.total_qubits is not None:
+        g_bits = int(round(np.log2(args.gpus)))
+        args.qubits = args.total_qubits - g_bits
+        args.scaling = "strong"
     if args.impl == "reference":
         run_reference_arm(args)
     else:
