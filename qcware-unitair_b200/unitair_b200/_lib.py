@@ -17,6 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libunitair_b200.so")
 
 UA_C64, UA_C128 = 0, 1
+UA_ERR_UNSUPPORTED = 2
 MAX_GATE_QUBITS = 5
 MAX_GENERIC_GATE_QUBITS = 10
 MAX_FUSED_GATES = 64
@@ -73,6 +74,11 @@ def _declare(L):
     L.ua_apply_fused_pass.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                       p_int, c_int, p_int, p_int, p_ll, c_void_p, c_longlong,
                                       c_int, c_void_p]
+    L.ua_apply_fused_pass_hostmats.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
+                                               p_int, c_int, p_int, p_int, p_ll, c_void_p, c_int, c_void_p]
+    L.ua_apply_fused_pass_scatter_hostmats.argtypes = [c_int, c_void_p, c_longlong, c_int, c_int, c_int, p_int,
+                                                       c_int, p_int, p_int, p_ll, c_void_p, c_int, p_int,
+                                                       POINTER(c_void_p), c_int, c_void_p]
     L.ua_fused_backward_pass.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                          p_int, c_int, p_int, p_int, p_ll, c_void_p, c_longlong,
                                          p_int, c_void_p, c_void_p]
@@ -91,7 +97,8 @@ def _declare(L):
     for name in ("ua_apply_sign_masks", "ua_apply_gate", "ua_gate_grad", "ua_apply_phase", "ua_phase_backward",
                  "ua_abs_squared", "ua_norm_squared", "ua_diag_expectation", "ua_inner_product",
                  "ua_fused_limits", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits",
-                 "ua_apply_fused_pass_scatter", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close",
+                 "ua_apply_fused_pass_scatter", "ua_apply_fused_pass_hostmats",
+                 "ua_apply_fused_pass_scatter_hostmats", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close",
                  "ua_sample_block_sums", "ua_sample_locate"):
         getattr(L, name).restype = c_int
 

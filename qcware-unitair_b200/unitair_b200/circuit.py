@@ -37,21 +37,24 @@ class TileGeometry:
     max_high: int        # H = T - L
     elem_bits: int = 0   # log2(8-byte TMA elements per amplitude): 0 complex64, 1 complex128
     max_windows: int = 5  # TMA tensor rank limit (see count_windows)
+    split_low: int = 0   # register-blocked path: the first TMA dimension is exactly the 4 lowest
+    #                      element bits (one 128-byte row, 128-byte shared-memory swizzle)
 
 
-def count_windows(low_bits: int, high, elem_bits: int = 0) -> int:
+def count_windows(low_bits: int, high, elem_bits: int = 0, split_low: int = 0) -> int:
     """Number of TMA box dimensions needed for the tile {0..low_bits-1} U high.
 
     A dimension covers a run of consecutive (8-byte element) index bits, at most 8 of them
-    (box extent <= 256).  Mirrors setup_tensor_maps() in csrc/ua_tile.cu: with at most 5
-    dimensions a tile moves with ONE cp.async.bulk.tensor instruction, otherwise the kernel
-    falls back to one bulk copy per contiguous run (much slower to issue).
+    (box extent <= 256); with split_low > 0 a new dimension starts at element bit split_low.
+    Mirrors setup_tensor_maps() in csrc/ua_tile.cu: with at most 5 dimensions a tile moves with
+    ONE cp.async.bulk.tensor instruction, otherwise the kernel falls back to one bulk copy per
+    contiguous run (much slower to issue; the register-blocked path refuses the pass).
     """
     pos = list(range(low_bits + elem_bits)) + [h + elem_bits for h in sorted(high)]
     n = 0
     start = length = None
     for b in pos:
-        if n and b == start + length and length < 8:
+        if n and b == start + length and length < 8 and not (split_low and b == split_low):
             length += 1
         else:
             n += 1
@@ -66,13 +69,23 @@ class Pass:
     direct: bool = False                                # single big gate -> direct kernel
 
 
-def default_geometry(num_qubits: int, dtype: torch.dtype) -> TileGeometry:
+def default_geometry(num_qubits: int, dtype: torch.dtype, cluster: bool = False) -> TileGeometry:
     """Tile shape used for a state of `num_qubits` qubits.
 
     complex64: 2^13 amplitudes = 64 KiB per tile (3 tiles resident per SM), complex128:
     2^12 = 64 KiB.  The low 7 (c64) / 6 (c128) bits are always in the tile, which makes
     every global access a coalesced 1 KiB run.
+    cluster=True: the register-blocked complex64 pass (ua_apply_fused_pass_hostmats): 2^12
+    amplitudes = 32 KiB per tile, seven tile buffers per SM (three being computed on, four in
+    flight to or from HBM), 128-byte swizzled rows.
     """
+    if cluster and dtype == torch.complex64:
+        tile = int(os.environ.get("UA_CLUSTER_TILE_BITS", 12))
+        low = 7
+        tile = min(tile, num_qubits)
+        low = min(low, tile)
+        split = 4 if (os.environ.get("UA_CLUSTER_SWZ", "1") != "0" and low >= 4) else 0
+        return TileGeometry(num_qubits, tile, low, tile - low, 0, split_low=split)
     if dtype == torch.complex128:
         tile, low, ebits = 12, 6, 1
     else:
@@ -169,7 +182,7 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
                 continue
             need = {b for b in bits if b >= geo.low_bits} - high
             if (len(high) + len(need) > geo.max_high or mat_elems + 4 ** k > max_mat_elems
-                    or (need and count_windows(geo.low_bits, high | need, geo.elem_bits) > geo.max_windows)):
+                    or (need and count_windows(geo.low_bits, high | need, geo.elem_bits, geo.split_low) > geo.max_windows)):
                 blocked.update(bits)
                 continue
             high |= need
@@ -190,7 +203,7 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             free = [p for p in range(geo.low_bits, geo.total_bits) if p not in high and p not in banned]
             if not free:
                 break
-            best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits), p))
+            best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits, geo.split_low), p))
             high.add(best)
         cur.high = sorted(high)
         passes.append(cur)
@@ -230,6 +243,13 @@ def _bkron(a, b):
     b4 = b.unsqueeze(-2).unsqueeze(-4)          # (..., 1, k, 1, l)
     out = a4 * b4
     return out.reshape(out.shape[:-4] + (out.shape[-4] * out.shape[-3], out.shape[-2] * out.shape[-1]))
+
+
+def use_cluster_path() -> bool:
+    """The register-blocked pass kernel (matrix values as kernel parameters) is the default for
+    complex64 circuits of shared 1-/2-qubit gates; UA_CLUSTER=0 keeps every pass on the
+    shared-memory-matrix kernel (A/B measurements)."""
+    return os.environ.get("UA_CLUSTER", "1") != "0"
 
 
 def default_merge_k() -> int:
@@ -301,11 +321,12 @@ def merge_gates(gates, max_k: int = None):
 class _PassLaunch:
     """Pre-marshalled arguments of one native call (everything except the state pointers)."""
 
-    __slots__ = ("direct", "gate", "low", "nhigh", "high", "ngates", "ks", "bits", "offs")
+    __slots__ = ("direct", "gate", "low", "nhigh", "high", "ngates", "ks", "bits", "offs", "host_ok")
 
     def __init__(self, p: Pass, geo: TileGeometry, gate_bits, offsets):
         self.direct = p.direct
         self.gate = p.gates[0] if p.direct else -1
+        self.host_ok = False
         if p.direct:
             return
         self.low = geo.tile_bits - len(p.high)
@@ -322,6 +343,8 @@ class _PassLaunch:
             flat += b + [0] * (3 - len(b))
         self.bits = L.int_array(flat)
         self.offs = L.ll_array([offsets[g] for g in p.gates])
+        # register-blocked path (matrices as kernel parameters): 1-/2-qubit gates, tile >= 4 bits
+        self.host_ok = geo.tile_bits >= 4 and all(len(gate_bits[g]) <= 2 for g in p.gates)
 
 
 def _pack_gates(mats_list, batch_shape):
@@ -371,12 +394,20 @@ class CompiledCircuit:
             if m.dim() != 2 and tuple(m.shape[:-2]) != self.batch_shape:
                 raise RuntimeError(f"operator batch dims {tuple(m.shape[:-2])} do not match the "
                                    f"state batch dims {self.batch_shape}")
-        if self.gates:
+        # gate tensors may all live on the host (merged there, no device synchronisation at all)
+        # or all on one CUDA device (merged there; the register-blocked path then needs ONE
+        # device-to-host copy of the merged matrices at compile time)
+        self.gates_on_host = bool(self.gates) and all(m.device.type == "cpu" for _, m in self.gates)
+        if self.gates and not self.gates_on_host:
             L.require_cuda(*[m for _, m in self.gates])
         if merge and os.environ.get("UA_MERGE_GATES", "1") != "0":
             with torch.no_grad():
                 self.gates = merge_gates(self.gates)
-        self.geo = geometry or default_geometry(n, dtype)
+        # register-blocked path: complex64, shared (un-batched) gates, matrix values on the host
+        self.cluster = (dtype == torch.complex64 and use_cluster_path() and bool(self.gates)
+                        and all(m.dim() == 2 for _, m in self.gates)
+                        and any(len(qs) <= 2 for qs, _ in self.gates))
+        self.geo = geometry or default_geometry(n, dtype, cluster=self.cluster)
         self.gate_bits = [[n - 1 - q for q in qs] for qs, _ in self.gates]
         if not self.gates:
             self.passes = []
@@ -391,11 +422,30 @@ class CompiledCircuit:
                                                                   self.batch_shape)
         self.launches = [_PassLaunch(p, self.geo, self.gate_bits, self.offsets) for p in self.passes]
         self._direct = {}
-        for pl in self.launches:
-            if pl.direct:
-                qs, m = self.gates[pl.gate]
-                self._direct[pl.gate] = (_engine._aligned(m), L.int_array(qs), len(qs),
-                                         0 if m.dim() == 2 else 4 ** len(qs))
+        self._dev_mats = {}         # device -> packed matrices there (fallback kernel, direct launches)
+        # matrix VALUES on the host feed the register-blocked pass kernel (they travel as kernel
+        # parameters): complex64, shared gates only
+        self.mats_host = None
+        if self.cluster and self.row_stride == 0 and any(pl.host_ok for pl in self.launches):
+            self.mats_host = self.mats if self.gates_on_host else self.mats.cpu()
+            self._mats_host_ptr = self.mats_host.data_ptr()
+
+    def _device_mats(self, dev):
+        """Packed matrices on `dev` (uploaded once when the gates were given on the host)."""
+        m = self._dev_mats.get(dev)
+        if m is None:
+            m = self.mats if self.mats.device == dev else self.mats.to(dev)
+            self._dev_mats[dev] = m
+        return m
+
+    def _direct_args(self, gate, dev):
+        key = (gate, dev)
+        d = self._direct.get(key)
+        if d is None:
+            qs, m = self.gates[gate]
+            d = (_engine._aligned(m.to(dev)), L.int_array(qs), len(qs), 0 if m.dim() == 2 else 4 ** len(qs))
+            self._direct[key] = d
+        return d
 
     def capture_graph(self, state: torch.Tensor):
         """Capture `run(state, in_place=True)` into a CUDA graph bound to `state`'s buffer.
@@ -449,16 +499,29 @@ class CompiledCircuit:
         total = self.batch << n
         with L.on_device(dev):
             stream = L.stream_ptr(dev)
-            mats_ptr = self.mats.data_ptr()
+            mats_ptr = None
             for pl in launches:
                 if pl.direct:
-                    m, qarr, k, gstride = self._direct[pl.gate]
+                    m, qarr, k, gstride = self._direct_args(pl.gate, dev)
                     L.check(lib.ua_apply_gate(code, out.data_ptr(), src.data_ptr(), m.data_ptr(), n, k,
                                               qarr, self.batch, 1 << n, gstride, 0, stream))
-                else:
-                    L.check(lib.ua_apply_fused_pass(
+                    src = out
+                    continue
+                if pl.host_ok and self.mats_host is not None:
+                    rc = lib.ua_apply_fused_pass_hostmats(
                         code, out.data_ptr(), src.data_ptr(), total, n, pl.low, pl.nhigh, pl.high,
-                        pl.ngates, pl.ks, pl.bits, pl.offs, mats_ptr, self.row_stride, 0, stream))
+                        pl.ngates, pl.ks, pl.bits, pl.offs, self._mats_host_ptr, 0, stream)
+                    if rc == 0:
+                        src = out
+                        continue
+                    if rc != L.UA_ERR_UNSUPPORTED:
+                        L.check(rc)
+                    pl.host_ok = False           # e.g. the tile needs > 5 TMA dimensions
+                if mats_ptr is None:
+                    mats_ptr = self._device_mats(dev).data_ptr()
+                L.check(lib.ua_apply_fused_pass(
+                    code, out.data_ptr(), src.data_ptr(), total, n, pl.low, pl.nhigh, pl.high,
+                    pl.ngates, pl.ks, pl.bits, pl.offs, mats_ptr, self.row_stride, 0, stream))
                 src = out
 
 
@@ -470,7 +533,7 @@ def _fill_high(high, geo: TileGeometry, forbidden=()):
         free = [p for p in range(geo.low_bits, geo.total_bits) if p not in high and p not in forbidden]
         if not free:
             return None
-        best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits), p))
+        best = min(free, key=lambda p: (count_windows(geo.low_bits, high | {p}, geo.elem_bits, geo.split_low), p))
         high.add(best)
     return sorted(high)
 
@@ -534,9 +597,19 @@ class ScatterTail:
         pl = self.launch
         dev = state.device
         with L.on_device(dev):
+            if pl.ngates and pl.host_ok and cc.mats_host is not None:
+                rc = L.lib().ua_apply_fused_pass_scatter_hostmats(
+                    L.dtype_code(self.dtype), state.data_ptr(), 1 << self.n, self.n, pl.low, pl.nhigh, pl.high,
+                    pl.ngates, pl.ks, pl.bits, pl.offs, cc._mats_host_ptr,
+                    self.m, self.victims, L.ptr_array(list(dst_ptrs)), int(visit_xor), L.stream_ptr(dev))
+                if rc == 0:
+                    return
+                if rc != L.UA_ERR_UNSUPPORTED:
+                    L.check(rc)
+                pl.host_ok = False
             L.check(L.lib().ua_apply_fused_pass_scatter(
                 L.dtype_code(self.dtype), state.data_ptr(), 1 << self.n, self.n, pl.low, pl.nhigh, pl.high,
-                pl.ngates, pl.ks, pl.bits, pl.offs, cc.mats.data_ptr() if pl.ngates else None,
+                pl.ngates, pl.ks, pl.bits, pl.offs, cc._device_mats(dev).data_ptr() if pl.ngates else None,
                 self.m, self.victims, L.ptr_array(list(dst_ptrs)), int(visit_xor), L.stream_ptr(dev)))
 
 
