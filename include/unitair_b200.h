@@ -153,6 +153,28 @@ int ua_apply_fused_pass_scatter(int dtype, const void *in, long long total_amps,
                                 int num_scatter_bits, const int *host_scatter_pos,
                                 void *const *host_dst_ptrs, int visit_xor, void *stream);
 
+/* The same two passes for complex64 circuits of SHARED 1-/2-qubit gates whose matrix VALUES are
+ * known on the host (host_gate_mats: host memory, interleaved re,im floats, same packing and
+ * offsets as gate_mats above).  The matrices travel in the kernel parameters and stay in uniform
+ * registers; the gates are applied to register-resident groups of 16 amplitudes ("clusters" of
+ * four tile bits, one shared-memory round trip per cluster instead of per gate); three
+ * 256-thread teams per SM work on a ring of tile buffers that a producer warp keeps in flight
+ * to and from HBM (csrc/ua_cluster.cu).  Returns UA_ERR_UNSUPPORTED when the pass does not fit
+ * this path (a gate with k > 2, complex128, a tile below 4 bits or above 2^12 amplitudes, more
+ * than 5 TMA dimensions with the first one fixed to the 4 lowest bits): call the device-matrix
+ * entry point instead.                                                                        */
+int ua_apply_fused_pass_hostmats(int dtype, void *out, const void *in, long long total_amps,
+                                 int total_bits, int tile_low_bits, int num_high,
+                                 const int *host_high_pos, int num_gates, const int *host_gate_k,
+                                 const int *host_gate_bits, const long long *host_gate_offset,
+                                 const void *host_gate_mats, int adjoint, void *stream);
+int ua_apply_fused_pass_scatter_hostmats(int dtype, const void *in, long long total_amps, int total_bits,
+                                         int tile_low_bits, int num_high, const int *host_high_pos,
+                                         int num_gates, const int *host_gate_k, const int *host_gate_bits,
+                                         const long long *host_gate_offset, const void *host_gate_mats,
+                                         int num_scatter_bits, const int *host_scatter_pos,
+                                         void *const *host_dst_ptrs, int visit_xor, void *stream);
+
 /* Peer memory for the scatter pass: export a device allocation of this process / map one of
  * another process on the same node (CUDA IPC).  ua_ipc_export writes a 64-byte handle for the
  * allocation containing `ptr` and the offset of `ptr` inside it; ua_ipc_open maps the peer's

@@ -120,6 +120,13 @@ template <bool STREAM> __device__ __forceinline__ void st32(double2 *p, const do
         asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
 }
 
+// SMs of the current device (grid caps are multiples of this, never a literal 148)
+static inline int sm_count() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms > 0 ? sms : 148;
+}
+
 static inline bool is_pow2(long long x) { return x > 0 && (x & (x - 1)) == 0; }
 static inline int ilog2(long long x) { int r = 0; while ((1ll << (r + 1)) <= x) ++r; return r; }
 

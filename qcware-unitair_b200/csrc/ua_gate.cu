@@ -447,7 +447,7 @@ extern "C" int ua_apply_gate(int dtype, void *out, const void *in, const void *g
             for (int i = 0; i < k; ++i) { d.spos[i] = pos[order[i]]; d.gbit[i] = k - 1 - order[i]; }
             d.num_batches = (batch * (dim >> k)) / 8;
             long long blocks = (d.num_batches + 7) / 8;
-            const long long cap = 148ll * 8;
+            const long long cap = (long long)sm_count() * 8;
             if (blocks > cap) blocks = cap;
             if (k == 4) gate_dmma_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(d);
             else gate_dmma_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(d);

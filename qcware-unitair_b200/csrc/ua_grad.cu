@@ -151,7 +151,7 @@ static GradPlan plan_grad(int dtype, int n, int k, long long batch, long long ga
     const bool per_batch = gate_bstride != 0;
     p.nseg = per_batch ? batch : 1;
     p.tiles_per_seg = per_batch ? p.tiles_per_state : p.tiles_per_state * batch;
-    long long want = (148ll * 4) / p.nseg;
+    long long want = ((long long)sm_count() * 4) / p.nseg;
     if (want < 1) want = 1;
     if (want > p.tiles_per_seg) want = p.tiles_per_seg;
     p.bps = (int)want;

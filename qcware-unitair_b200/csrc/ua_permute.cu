@@ -69,7 +69,7 @@ extern "C" int ua_permute_bits(int dtype, void *out, const void *in, int num_bit
     const int shift = vec ? 1 : 0;
     const long long count = a.total >> shift;
     long long blocks = (count + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    { const long long cap = (long long)sm_count() * 16; if (blocks > cap) blocks = cap; }
     if (dtype == UA_C64) {
         if (vec) permute_bits_kernel<float4><<<(unsigned)blocks, 256, 0, st>>>(a, 1);
         else permute_bits_kernel<float2><<<(unsigned)blocks, 256, 0, st>>>(a, 0);

@@ -119,7 +119,7 @@ static int fill_args(PhaseArgs &a, int dtype, long long elems, long long batch,
 
 static unsigned scalar_grid(long long total) {
     long long blocks = (total + 255) / 256;
-    const long long cap = 148ll * 64;
+    const long long cap = (long long)sm_count() * 64;
     return (unsigned)(blocks < cap ? blocks : cap);
 }
 

@@ -172,10 +172,10 @@ extern "C" int ua_abs_squared(int dtype, void *out_real, const void *in, long lo
             abs2_vec_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float2 *>(out_real), reinterpret_cast<const float4 *>(in), nvec);
             return check_launch("abs2_vec_kernel");
         }
-        long long blocks = (count + 255) / 256; if (blocks > 148 * 64) blocks = 148 * 64;
+        long long blocks = (count + 255) / 256; { const long long cap = (long long)sm_count() * 64; if (blocks > cap) blocks = cap; }
         abs2_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float *>(out_real), reinterpret_cast<const float2 *>(in), count);
     } else if (dtype == UA_C128) {
-        long long blocks = (count + 255) / 256; if (blocks > 148 * 64) blocks = 148 * 64;
+        long long blocks = (count + 255) / 256; { const long long cap = (long long)sm_count() * 64; if (blocks > cap) blocks = cap; }
         abs2_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<double *>(out_real), reinterpret_cast<const double2 *>(in), count);
     } else { set_error("ua_abs_squared: bad dtype"); return UA_ERR_INVALID; }
     return check_launch("abs2_kernel");

@@ -109,14 +109,18 @@ __global__ void __launch_bounds__(256) sample_locate_kernel(const typename CplxO
     const double excl = incl - mine;
     const double r_owner = r - __shfl_sync(0xffffffffu, excl, owner);
     if (lane == owner) {
+        // if rounding leaves r_owner at or above the lane's own sum, fall back to the LAST amplitude
+        // with non-zero probability (never an amplitude that cannot be measured)
         double acc = 0.0;
-        long long idx = myhi - 1;
+        long long idx = -1, last_nonzero = myhi - 1;
         for (long long i = mylo; i < myhi; ++i) {
             const auto x = in[i];
-            acc += (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+            const double pr = (double)x.x * (double)x.x + (double)x.y * (double)x.y;
+            acc += pr;
+            if (pr > 0.0) last_nonzero = i;
             if (acc > r_owner) { idx = i; break; }
         }
-        out[s] = idx;
+        out[s] = idx >= 0 ? idx : last_nonzero;
     }
 }
 

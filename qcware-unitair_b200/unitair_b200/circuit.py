@@ -84,7 +84,7 @@ def default_geometry(num_qubits: int, dtype: torch.dtype, cluster: bool = False)
         low = 7
         tile = min(tile, num_qubits)
         low = min(low, tile)
-        split = 4 if (os.environ.get("UA_CLUSTER_SWZ", "1") != "0" and low >= 4) else 0
+        split = 4 if low >= 4 else 0          # smaller tiles fall back to the shared-memory-matrix kernel
         return TileGeometry(num_qubits, tile, low, tile - low, 0, split_low=split)
     if dtype == torch.complex128:
         tile, low, ebits = 12, 6, 1
@@ -192,10 +192,17 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             if len(blocked) >= geo.total_bits:
                 break
         if not cur.gates:
-            # nothing fits under the ban (the first gate touches a forbidden bit): an empty first
-            # pass would loop forever -- lift the ban, the caller copes (extra copy pass)
-            forbidden = set()
-            passes.append(None)
+            if banned:
+                # nothing fits under the ban (the first gate touches a forbidden bit): lift the
+                # ban, the caller copes (extra copy pass)
+                forbidden = set()
+                passes.append(None)
+                continue
+            # no ban and the first pending gate still does not fit a tile (tiny max_high, too
+            # many TMA windows, a matrix budget below one gate): run it through the single-gate
+            # kernel instead of spinning
+            passes.append(Pass(high=[], gates=[first], direct=True))
+            done[first] = True
             continue
         # fill the unused high slots so the tile is full: first positions that keep the number
         # of TMA dimensions (extend an existing run), then anything
@@ -503,8 +510,13 @@ class CompiledCircuit:
             for pl in launches:
                 if pl.direct:
                     m, qarr, k, gstride = self._direct_args(pl.gate, dev)
-                    L.check(lib.ua_apply_gate(code, out.data_ptr(), src.data_ptr(), m.data_ptr(), n, k,
+                    dst = out
+                    if k > L.MAX_GATE_QUBITS and src.data_ptr() == out.data_ptr():
+                        dst = torch.empty_like(out)      # the generic 6..10-qubit kernel is out-of-place only
+                    L.check(lib.ua_apply_gate(code, dst.data_ptr(), src.data_ptr(), m.data_ptr(), n, k,
                                               qarr, self.batch, 1 << n, gstride, 0, stream))
+                    if dst is not out:
+                        out.copy_(dst)
                     src = out
                     continue
                 if pl.host_ok and self.mats_host is not None:
@@ -698,6 +710,8 @@ class _AdjointCircuit(torch.autograd.Function):
                                     it = torch.tensor(idx, device=dev)
                                     blk = blk.index_select(-2, it).index_select(-1, it)
                                 gm = mats[gi]
+                                if gm.dim() == 2 and rows > 1:
+                                    blk = blk.sum(0)      # a shared gate next to per-entry gates: sum over the batch
                                 grads[gi] = blk.to(gm.dtype).reshape(gm.shape)
                             off += d * d
         grad_state = g if ctx.needs_input_grad[0] else None
@@ -709,7 +723,8 @@ def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torc
     """Apply an ordered list of (qubits, operator) to a state in vector layout.
 
     Equivalent to calling simulation.apply_operator for each gate in turn.  Operators are
-    (2^k, 2^k) or share the state's batch dims.  When no gradient is needed the list is
+    (2^k, 2^k) or share the state's batch dims; they live on the state's device or (all of them,
+    no autograd) on the host.  When no gradient is needed the list is
     executed as fused shared-memory passes.  With autograd it runs one native gate kernel and
     one autograd node per gate (one saved state per gate that needs a gradient, like torch's
     tape through the reference) -- unless assume_unitary=True, which differentiates the whole
@@ -740,7 +755,12 @@ def apply_gates(gates: Sequence[Tuple[Sequence[int], torch.Tensor]], state: torc
         for qs, m in gates:
             out = ops.apply_operator(m, qs, out)
         return out
-    L.require_cuda(state, *[m for _, m in gates])
+    if gates and all(m.device.type == "cpu" for _, m in gates):
+        # host operators (an extension of the reference's contract): merged on the host, their
+        # values go to the pass kernel as launch parameters -- no upload, no synchronisation
+        L.require_cuda(state)
+    else:
+        L.require_cuda(state, *[m for _, m in gates])
     return CompiledCircuit(gates, n, state.dtype, batch_shape).run(state, in_place=in_place)
 
 

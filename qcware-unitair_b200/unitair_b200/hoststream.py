@@ -67,9 +67,15 @@ class HostCircuitStream:
             buf.copy_(h_in, non_blocking=True)
             d_gates = None
             if compiled is None:
-                d_gates = [(qs, u.to(self.device, non_blocking=True)) for qs, u in gates]
-                for _, u in d_gates:
-                    u.record_stream(self.s_run)      # allocated on s_in, consumed on s_run
+                if all(u.device.type == "cpu" for _, u in gates):
+                    # host operators: merged on the host, their values feed the register-blocked
+                    # pass kernel as launch parameters -- nothing to upload, no synchronisation
+                    d_gates = [(qs, u) for qs, u in gates]
+                else:
+                    d_gates = [(qs, u.to(self.device, non_blocking=True)) for qs, u in gates]
+                    for _, u in d_gates:
+                        if u.device.type == "cuda":
+                            u.record_stream(self.s_run)      # allocated on s_in, consumed on s_run
             ev_in = torch.cuda.Event()
             ev_in.record(self.s_in)
         with torch.cuda.stream(self.s_run):

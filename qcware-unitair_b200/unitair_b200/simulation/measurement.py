@@ -43,6 +43,13 @@ def sample_indices(state: torch.Tensor, num_samples: int, generator: Optional[to
         stream = L.stream_ptr(dev)
         L.check(lib.ua_sample_block_sums(code, sums.data_ptr(), st.data_ptr(), elems, blog, stream))
         cdf = torch.cumsum(sums, 0)
+        # the reference's Categorical refuses a probability vector that is all zero or not finite
+        # (src/unitair/simulation/measurement.py:43); sampling returns host data anyway, so the
+        # synchronisation costs nothing extra
+        total = float(cdf[-1])
+        if not (total > 0.0) or total == float("inf"):
+            raise ValueError("measure: the state has no finite, non-zero norm (sum of |amplitude|^2 = "
+                             f"{total}); probabilities cannot be formed")
         if uniforms is None:
             uniforms = torch.rand(num_samples, dtype=torch.float64, device=dev, generator=generator)
         else:

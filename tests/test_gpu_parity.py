@@ -866,7 +866,11 @@ def test_host_circuit_stream_matches_apply_gates(ua):
     hs.drain()
     for gl, h_in, h_out in jobs:
         ref = ua.circuit.apply_gates([(qs, u.cuda()) for qs, u in gl], h_in.cuda())
-        assert torch.equal(torch.view_as_real(h_out), torch.view_as_real(ref.cpu()))
+        # host operators are merged on the host (no upload, no synchronisation), device operators
+        # on the device: the merged 4x4 products differ in the last bit, the states by ~1e-7
+        assert_close(h_out.numpy(), host(ref), "c64")
+        same = ua.circuit.apply_gates(gl, h_in.cuda())            # host operators here too: bit-exact
+        assert torch.equal(torch.view_as_real(h_out), torch.view_as_real(same.cpu()))
     # a compiled plan can be reused, and a second round after drain() works
     cc = None
     outs = [torch.empty(2 ** n, dtype=torch.complex64).pin_memory() for _ in range(4)]

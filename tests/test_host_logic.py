@@ -191,3 +191,25 @@ def test_scatter_tail_copy_pass_geometry():
         circuit.ScatterTail(None, 30, torch.complex64, [3])          # a leaving bit among the low bits
     assert circuit._fill_high({9}, circuit.TileGeometry(10, 8, 7, 1), forbidden=[]) == [9]
     assert circuit._fill_high(set(), circuit.TileGeometry(9, 9, 7, 2), forbidden=[8]) is None
+
+
+def test_plan_passes_never_spins_when_a_gate_cannot_fit():
+    """a gate that fits no tile (no room for its high bits) must become a direct
+    launch instead of looping forever."""
+    geo = circuit.TileGeometry(12, 5, 4, 1)              # one free high slot only
+    gate_bits = [[0, 1], [8, 9], [2, 10], [9, 11, 3]]     # the 2nd and 4th need two high bits
+    passes = circuit.plan_passes(gate_bits, geo)
+    seen = sorted(g for p in passes for g in p.gates)
+    assert seen == [0, 1, 2, 3]
+    assert any(p.direct and p.gates == [1] for p in passes)
+
+
+def test_cluster_geometry_and_window_split():
+    g = circuit.default_geometry(30, torch.complex64, cluster=True)
+    assert (g.tile_bits, g.low_bits, g.max_high, g.split_low) == (12, 7, 5, 4)
+    # the first TMA dimension is exactly bits 0..3; bits 4.. continue as before
+    assert circuit.count_windows(7, [7, 8, 9, 10, 11], 0, split_low=4) == 2
+    assert circuit.count_windows(7, [7, 8, 9, 10, 11], 0) == 2          # 0..7 and 8..11
+    assert circuit.count_windows(7, [9, 11, 13, 15, 17], 0, split_low=4) == 7
+    small = circuit.default_geometry(3, torch.complex64, cluster=True)
+    assert small.split_low == 0 and small.tile_bits == 3
