@@ -141,7 +141,9 @@ def load_reference():
 
 
 def cpu_layer_rate(n, layers, seed, reps, warm):
-    """gate-amplitude updates/s of the reference's CPU path on an n-qubit sample."""
+    """gate-amplitude updates/s of the reference's CPU path (simulation.apply_operator once per
+    gate, /root/reference/src/unitair/simulation/operations.py:45) on an n-qubit sample of the
+    bench recipe, with every host core torch can use."""
     import torch
     kind, mod = load_reference()
     cores = os.cpu_count() or 1
@@ -176,27 +178,36 @@ def cpu_layer_rate(n, layers, seed, reps, warm):
         if i >= warm:
             times.append(dt)
     updates = len(gates) * float(2 ** n)
+    what = ("unmodified reference (baseline/_ref, unitair.simulation.apply_operator per gate)" if kind == "reference"
+            else "numpy port of the reference (oracle/unitair_oracle.py; baseline/_ref did not travel)")
     return {"value": updates / float(np.median(times)), "unit": UNIT, "cores": threads,
-            "kind": kind,
-            "sample": f"{layers} layer(s) of the same recipe ({len(gates)} gates) on a {n}-qubit "
-                      f"complex64 state, median of {reps} after {warm} warm-up, torch CPU threads={threads}"
-            }, float(np.median(times))
+            "host_cores": cores, "kind": kind,
+            "sample": f"{what}: {layers} layer(s) of the bench recipe ({len(gates)} gates) on a {n}-qubit "
+                      f"complex64 state, median of {reps} after {warm} warm-up, torch CPU threads={threads}",
+            "sample_qubits": n, "sample_layers": layers, "sample_gates": len(gates),
+            "sample_seconds": float(np.median(times))}, float(np.median(times))
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host
+    cores.  A step of this arm is a BOUNDED SAMPLE of the workload (the 30-qubit state would need
+    ~40 GiB and minutes per layer on the host): `config` names both the workload the other arm
+    runs and the sample that was timed here; value is updates/s, which is size-independent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n = args.cpu_qubits
-    t_all = []
-    base, t_step = cpu_layer_rate(n, 1, args.seed, reps=max(1, args.steps), warm=max(1, min(args.warmup, 2)))
+    base, t_step = cpu_layer_rate(n, args.cpu_layers, args.seed, reps=max(1, args.steps),
+                                  warm=max(1, min(args.warmup, 2)))
+    cfg = workload_config(args, args.gpus)
+    cfg["timed_sample"] = {"qubits": n, "layers": args.cpu_layers, "gates": base["sample_gates"],
+                           "note": "ms_per_step is one pass over this sample, not over the workload above"}
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "c64", "data": "synthetic",
-        "config": workload_config(args, args.gpus),
-        "cpu_baseline": base,
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": t_step * 1e3, "step_is_sample": True, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+        "config": cfg, "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -214,6 +225,155 @@ def workload_config(args, n_gpus):
         "parallelism": "single GPU" if n_gpus == 1 else f"state sharded over {n_gpus} GPUs (global-qubit swaps)",
         "l2_policy": f"inputs larger than L2 ({8 * 2 ** args.qubits / 2 ** 30:.0f} GiB state per GPU vs 126 MB L2)",
     }
+
+
+
+class gpu_local_cpus:
+    """Run a block on the host cores next to a GPU (sysfs local_cpulist of its PCI device), so
+    that pinned buffers allocated inside it are first-touched on the GPU's NUMA node."""
+
+    def __init__(self, index):
+        self.index = index
+        self.old = None
+        self.info = None
+
+    def __enter__(self):
+        try:
+            bus = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=pci.bus_id",
+                                  "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+            dom, rest = bus.split(":", 1)
+            path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/local_cpulist"
+            cpus = set()
+            for part in open(path).read().strip().split(","):
+                if "-" in part:
+                    a, b = part.split("-")
+                    cpus.update(range(int(a), int(b) + 1))
+                elif part:
+                    cpus.add(int(part))
+            allowed = os.sched_getaffinity(0)
+            if cpus & allowed:
+                self.old = allowed
+                os.sched_setaffinity(0, cpus & allowed)
+                self.info = f"{len(cpus & allowed)} cores local to GPU {self.index}"
+        except Exception:
+            self.old = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            os.sched_setaffinity(0, self.old)
+        return False
+
+
+# --------------------------------------------------------------------------- multi-GPU helpers
+def sharded_parity_check(world, rank, dev, n_total=24, layers=3, seed=77):
+    """Correctness inside the artefact the driver runs: a 24-qubit circuit of the bench recipe on
+    the state sharded over all ranks, with BOTH exchange formulations (fused peer-memory stores,
+    bit permutation + NCCL send/recv), against the single-GPU engine on rank 0.  Returns a dict;
+    `ok` is False when any relative error exceeds the 1e-5 tolerance of BASELINE.json."""
+    import torch
+    import torch.distributed as dist
+    from unitair_b200 import circuit, sharded
+    gates_np = random_circuit(n_total, layers, seed)
+    gates = [(qs, torch.as_tensor(u.astype(np.complex64)).to(dev)) for qs, u in gates_np]
+    out = {"qubits": n_total, "layers": layers, "gates": len(gates), "tolerance": 1e-5, "ok": True}
+    ref = None
+    if rank == 0:
+        full = torch.zeros(2 ** n_total, dtype=torch.complex64, device=dev)
+        full[0] = 1
+        ref = circuit.CompiledCircuit(gates, n_total, torch.complex64).run(full, in_place=True)
+    for mode in ("p2p", "nccl"):
+        try:
+            st = sharded.ShardedState.zero_state(n_total, torch.complex64, dev)
+            sc = sharded.ShardedCircuit(gates, n_total, torch.complex64, world, restore=True, exchange=mode)
+            sc.run(st)
+            sc.run(st)                                   # replayable plan: apply it twice ...
+            got = st.gather_logical()
+            nrm = float(st.norm_squared().item())
+            if rank == 0:
+                twice = circuit.CompiledCircuit(gates, n_total, torch.complex64).run(ref.clone(), in_place=True)
+                err = float((torch.linalg.vector_norm(got - twice) / torch.linalg.vector_norm(twice)).item())
+                out[mode] = {"rel_err_vs_single_gpu": err, "norm_squared": nrm, "swaps": sc.num_swaps,
+                             "fused_swaps": sc.num_fused_swaps, "peer_stores": bool(sc.p2p)}
+                if not (err < 1e-5 and abs(nrm - 1) < 1e-4):
+                    out["ok"] = False
+            st.release_peers()
+            del st, sc, got
+        except Exception as e:  # pragma: no cover
+            out[mode] = {"error": repr(e)[:300]}
+            out["ok"] = False
+    flag = torch.tensor([1.0 if out["ok"] else 0.0], device=dev)
+    dist.broadcast(flag, src=0)
+    out["ok"] = bool(flag.item() > 0.5)
+    torch.cuda.empty_cache()
+    return out
+
+
+def timed_sharded_run(n_total, layers, seed, world, rank, dev, exchange_mode, warm, steps):
+    """The bench circuit on an n_total-qubit state over `world` ranks (world == 1: single-GPU
+    engine): device time per step (max over ranks), norm check after the timed steps."""
+    import torch
+    import torch.distributed as dist
+    from unitair_b200 import circuit, sharded, _lib
+    gates_np = random_circuit(n_total, layers, seed)
+    gates = [(qs, torch.as_tensor(u.astype(np.complex64)).to(dev)) for qs, u in gates_np]
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    if world == 1:
+        state = torch.zeros(2 ** n_total, dtype=torch.complex64, device=dev)
+        state[0] = 1
+        cc = circuit.CompiledCircuit(gates, n_total, torch.complex64)
+        for _ in range(warm):
+            cc.run(state, in_place=True)
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            cc.run(state, in_place=True)
+        e1.record()
+        torch.cuda.synchronize()
+        from unitair_b200.states import norm_squared
+        nrm = float(norm_squared(state).item())
+        elapsed = e0.elapsed_time(e1) / 1e3
+        info = {"passes_per_step": cc.num_passes}
+        launches = _lib.launch_count() - l0
+        del state
+    else:
+        sstate = sharded.ShardedState.zero_state(n_total, torch.complex64, dev)
+        plans, layout = [], sharded.identity_layout(n_total)
+        for _ in range(warm + steps):
+            pl_ = sharded.ShardedCircuit(gates, n_total, torch.complex64, world, layout=layout, restore=False,
+                                         exchange=exchange_mode)
+            plans.append(pl_)
+            layout = pl_.end_layout
+        for pl_ in plans[:warm]:
+            pl_.run(sstate)
+        dist.barrier()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0.record()
+        for pl_ in plans[warm:]:
+            pl_.run(sstate)
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - l0
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+        nrm = float(sstate.norm_squared().item())
+        timed = plans[warm:]
+        info = {"passes_per_step": sum(p_.num_passes for p_ in timed) / len(timed),
+                "swaps_per_step": sum(p_.num_swaps for p_ in timed) / len(timed),
+                "swap_bytes_per_gpu_per_step": sum(p_.swap_bytes_per_step for p_ in timed) / len(timed)}
+        sstate.release_peers()
+        del sstate, plans
+    torch.cuda.empty_cache()
+    updates = len(gates_np) * float(2 ** n_total)
+    info.update({"qubits": n_total, "n_gpus": world, "steps": steps, "warmup": warm,
+                 "ms_per_step": elapsed / steps * 1e3, "value": updates * steps / elapsed, "unit": UNIT,
+                 "norm_squared_after": nrm, "norm_ok": bool(abs(nrm - 1) < 1e-3), "gpu_launches": int(launches)})
+    return info
 
 
 # --------------------------------------------------------------------------- our arm
@@ -257,7 +417,7 @@ def run_ours(args):
         cc = circuit.CompiledCircuit(gates_dev, n_total, torch.complex64)
         step = lambda: cc.run(state, in_place=True)   # noqa: E731
         launches_per_step = cc.num_passes
-        kernel_name = "fused_pass_kernel"
+        kernel_name = "cluster_ring_kernel" if getattr(cc, "mats_host", None) is not None else "fused_pass_kernel"
         extra = {"passes_per_step": cc.num_passes, "gates_per_step": num_gates}
     else:
         from unitair_b200 import sharded
@@ -294,7 +454,7 @@ def run_ours(args):
         timed = plans[max(args.warmup, 3):max(args.warmup, 3) + args.steps]
         plan = plans[-1]
         launches_per_step = sum(p_.num_passes for p_ in timed) / len(timed)
-        kernel_name = "fused_pass_kernel"
+        kernel_name = "cluster_ring_kernel"
         extra = {"passes_per_step": launches_per_step, "gates_per_step": num_gates,
                  "swaps_per_step": sum(p_.num_swaps for p_ in timed) / len(timed),
                  "fused_swaps_per_step": sum(p_.num_fused_swaps for p_ in timed) / len(timed),
@@ -302,6 +462,9 @@ def run_ours(args):
                              else "nccl (bit permutation pass + grouped send/recv)",
                  "swap_bytes_per_gpu_per_step": sum(p_.swap_bytes_per_step for p_ in timed) / len(timed)}
 
+    check = None
+    if world > 1 and not args.no_check:
+        check = sharded_parity_check(world, rank, dev)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -344,6 +507,21 @@ def run_ours(args):
         "gpu_launches": int(launches), "clocks": clocks,
     }
     line.update(extra)
+    # correctness of what was just timed: the state is still normalised (unitary circuit) ...
+    if world == 1:
+        nrm = float(ua.norm_squared(state).item())
+    else:
+        nrm = float(sstate.norm_squared().item())
+    norm_ok = bool(abs(nrm - 1) < 1e-3)
+    if world > 1:
+        # ... and the sharded engine agrees with the single-GPU engine (both exchange modes)
+        if check is None:
+            check = {"ok": True, "skipped": "--no-check"}
+        check["norm_squared_after_timed_steps"] = nrm
+        check["ok"] = bool(check["ok"] and norm_ok)
+        line["check"] = check
+    else:
+        line["check"] = {"norm_squared_after_timed_steps": nrm, "ok": norm_ok}
     big = n_local > 31          # 32+ qubits per GPU: one state copy only, no pinned host mirror
     if big:
         line["skipped"] = "per_gate / e2e sections need extra state copies (>= 64 GiB each): skipped at this size"
@@ -352,10 +530,11 @@ def run_ours(args):
         # plans + runs the circuit through the public sharded API inside the timed region
         try:
             shard_elems = 2 ** n_local
-            h_in = torch.zeros(shard_elems, dtype=torch.complex64).pin_memory()
+            with gpu_local_cpus(local_rank) as numa:
+                h_in = torch.zeros(shard_elems, dtype=torch.complex64).pin_memory()
+                h_out = torch.zeros(shard_elems, dtype=torch.complex64).pin_memory()
             if rank == 0:
                 h_in[0] = 1
-            h_out = torch.empty(shard_elems, dtype=torch.complex64).pin_memory()
             h_gates = [(qs, torch.as_tensor(u.astype(np.complex64)).pin_memory()) for qs, u in gates_np]
             gate_bytes = sum(u.numel() * 8 for _, u in h_gates)
 
@@ -382,6 +561,7 @@ def run_ours(args):
                            "h2d_bytes_per_step": int((8 * shard_elems + gate_bytes) * world),
                            "d2h_bytes_per_step": int(8 * shard_elems * world), "steps": k_e2e,
                            "ms_per_step": t_e2e / k_e2e * 1e3,
+                           "pinned_buffers": numa.info or "default NUMA placement",
                            "what": "per rank: pinned host shard + gates -> device, ShardedCircuit "
                                    "(planning, merging, packing) + run, shard -> pinned host"}
             del h_in, h_out
@@ -394,9 +574,18 @@ def run_ours(args):
                                        restore=False, exchange=exchange_mode)
         tplan.run(sstate, timing=tm)
         line["phase_ms_per_step_rank0"] = {k: round(v, 2) for k, v in tm.items()}
-        if tm.get("exchange") and not tplan.p2p:
-            line["nvlink_GBs_per_gpu_per_direction"] = round(
-                tplan.swap_bytes_per_step / (tm["exchange"] / 1e3) / 1e9, 1)
+        nv = None
+        if tplan.p2p and tm.get("scatter_pass"):
+            # the passes whose stores cross NVLink: bytes leaving this GPU / their device time
+            nv = tplan.swap_bytes_per_step / (tm["scatter_pass"] / 1e3) / 1e9
+            what = "peer stores of the fused scatter passes (compute included in the pass time)"
+        elif tm.get("exchange") and not tplan.p2p:
+            nv = tplan.swap_bytes_per_step / (tm["exchange"] / 1e3) / 1e9
+            what = "NCCL send/recv exchange"
+        if nv is not None:
+            line["nvlink"] = {"GBs_per_gpu_per_direction": round(nv, 1), "frac_of_900": round(nv / 900.0, 3),
+                              "frac_of_measured_770": round(nv / 770.0, 3), "what": what,
+                              "bytes_per_gpu_per_step": tplan.swap_bytes_per_step}
 
     if world == 1 and not big:
         # ---- per-gate path (the reference's call pattern: one apply_operator per gate) ----
@@ -427,9 +616,10 @@ def run_ours(args):
     if world == 1 and not (big or args.no_e2e):
         # ---- end to end through the public API with host buffers -------------------------
         try:
-            h_state = torch.zeros(2 ** n_total, dtype=torch.complex64).pin_memory()
+            with gpu_local_cpus(local_rank) as numa:
+                h_state = torch.zeros(2 ** n_total, dtype=torch.complex64).pin_memory()
+                h_out = torch.zeros(2 ** n_total, dtype=torch.complex64).pin_memory()
             h_state[0] = 1
-            h_out = torch.empty(2 ** n_total, dtype=torch.complex64).pin_memory()
             h_gates = [(qs, torch.as_tensor(u.astype(np.complex64)).pin_memory()) for qs, u in gates_np]
             gate_bytes = sum(u.numel() * 8 for _, u in h_gates)
             del state
@@ -459,6 +649,7 @@ def run_ours(args):
                            "d2h_bytes_per_step": int(8 * 2 ** n_total), "steps": k_e2e,
                            "ms_per_step": t_e2e / k_e2e * 1e3,
                            "one_job_at_a_time_ms_per_step": t_serial * 1e3,
+                           "pinned_buffers": numa.info or "default NUMA placement",
                            "what": "HostCircuitStream.submit per step: pinned host state + gates -> device, "
                                    "planning + packing + fused passes, final state -> pinned host; upload of "
                                    "step k+1, circuit of step k and download of step k-1 overlap (3 streams, "
@@ -472,15 +663,41 @@ def run_ours(args):
         # ---- CPU baseline (reference's own path on this box's host cores) -----------------
         if not args.no_cpu_baseline:
             try:
-                base, _ = cpu_layer_rate(args.cpu_qubits, 1, args.seed, reps=2, warm=1)
+                base, _ = cpu_layer_rate(args.cpu_qubits, args.cpu_layers, args.seed, reps=3, warm=1)
                 line["cpu_baseline"] = base
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
 
+    # ---- extra sections (BASELINE config 5): the 33-qubit strong-scaling point of this GPU count
+    # and, on 8 GPUs, the 36-qubit run -- driver-visible, each with its own norm check
+    if not args.no_extra and args.total_qubits is None and args.qubits == 30:
+        try:
+            if world > 1:
+                sstate.release_peers()
+                dist.barrier()
+                sstate.local = sstate.spare = None
+                plans = tplan = None
+            else:
+                state = None
+            torch.cuda.empty_cache()
+            if world == 8:
+                line["strong_scaling_33q"] = {"qubits": 33, "n_gpus": 8, "ms_per_step": line["ms_per_step"],
+                                              "value": line["value"], "unit": UNIT,
+                                              "note": "identical to this run (33 qubits = 30 per GPU on 8 GPUs)"}
+                line["config5_36q"] = timed_sharded_run(36, args.layers, args.seed + 5, world, rank, dev,
+                                                        exchange_mode, warm=2, steps=2)
+            else:
+                line["strong_scaling_33q"] = timed_sharded_run(33, args.layers, args.seed, world, rank, dev,
+                                                               exchange_mode if world > 1 else None, warm=2, steps=3)
+        except Exception as e:  # pragma: no cover
+            line["extra_error"] = repr(e)[:300]
+    failed = not line["check"]["ok"]
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if failed:
+        raise SystemExit("bench: correctness check failed (see the `check` key)")
 
 
 def main():
@@ -498,6 +715,10 @@ def main():
     ap.add_argument("--seed", type=int, default=202)
     ap.add_argument("--cpu-qubits", type=int, default=24,
                     help="size of the bounded CPU sample for the reference arm")
+    ap.add_argument("--cpu-layers", type=int, default=2, help="layers of the bounded CPU sample")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the extra sections (33-qubit strong-scaling point, 36-qubit run at 8 GPUs)")
+    ap.add_argument("--no-check", action="store_true", help="skip the sharded-vs-single-GPU parity check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

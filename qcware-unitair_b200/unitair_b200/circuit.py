@@ -596,16 +596,19 @@ class ScatterTail:
     def num_passes(self):
         return len(self.inplace_launches) + 1
 
-    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None, visit_xor: int = 0):
+    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None, visit_xor: int = 0, mark=None):
         """In-place passes on `state`, then the tail pass from `state` into the 2^m destination
         blocks `dst_ptrs` (device addresses, possibly of peer GPUs).  `before_scatter` is called
         right before the scatter pass is enqueued (cross-rank fence when the destinations may
-        still be in use).  visit_xor: see ua_apply_fused_pass_scatter (rank-dependent tile order)."""
+        still be in use).  visit_xor: see ua_apply_fused_pass_scatter (rank-dependent tile order).
+        mark: optional callback(tag) for phase timing, called after the in-place passes."""
         cc = self.compiled
         if self.inplace_launches:
             cc._run_launches(self.inplace_launches, state, state)
         if before_scatter is not None:
             before_scatter()
+        if mark is not None:
+            mark("gates")
         pl = self.launch
         dev = state.device
         with L.on_device(dev):

@@ -227,6 +227,7 @@ class CudaEngine:
 
     # fused scatter exchange (peer-memory stores from the last pass of an epoch)
     supports_scatter = True
+    supports_scatter_mark = True
 
     def min_victim_bit(self, n_local, g):
         from . import circuit
@@ -237,7 +238,7 @@ class CudaEngine:
         from . import circuit
         return circuit.ScatterTail(compiled, n_local, self.dtype, victim_bits)
 
-    def run_scatter(self, tail, st, ep, before_scatter=None):
+    def run_scatter(self, tail, st, ep, before_scatter=None, mark=None):
         """The epoch's passes with the last one storing into the peers' spare buffers: block b of
         the exchange `ep` goes to block a (this rank's own value of the swapped rank bits) of the
         spare buffer of the rank whose swapped rank bits equal b."""
@@ -249,7 +250,7 @@ class CudaEngine:
         dst = [spare_of[exchange_peer(st.rank, ep, b)] + a * block_bytes for b in range(1 << m)]
         # visit order rotated by this rank's own block number: at any moment every rank of the
         # exchange group is writing to a different peer
-        tail.run(st.local, dst, before_scatter=before_scatter, visit_xor=a)
+        tail.run(st.local, dst, before_scatter=before_scatter, visit_xor=a, mark=mark)
 
     def permute(self, src_bits, shard, out):
         from . import _lib as L
@@ -536,11 +537,18 @@ class ShardedCircuit:
                     mark("exchange")
             tail = self.tails[i]
             if tail is not None:
-                self.engine.run_scatter(tail, st, self.epochs[i + 1],
-                                        before_scatter=None if spare_idle else (lambda: self._fence(st)))
+                if getattr(self.engine, "supports_scatter_mark", False):
+                    self.engine.run_scatter(tail, st, self.epochs[i + 1],
+                                            before_scatter=None if spare_idle else (lambda: self._fence(st)),
+                                            mark=mark)
+                    mark("scatter_pass")          # the pass whose stores cross NVLink
+                else:
+                    self.engine.run_scatter(tail, st, self.epochs[i + 1],
+                                            before_scatter=None if spare_idle else (lambda: self._fence(st)))
+                    mark("gates")
             else:
                 self.engine.run(comp, st.local)
-            mark("gates")
+                mark("gates")
         st.layout = list(self.end_layout)
         if marks:
             torch.cuda.synchronize()
