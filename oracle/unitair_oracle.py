@@ -261,6 +261,39 @@ def swap(state, qubit_pair):
     return permute_qubits(perm, state)
 
 
+def roll_qubits(state, num_steps=1):
+    """operations.py:540-597: rolled[a_0..a_{n-1}] = psi[a_k..a_{n-1}, a_0..a_{k-1}] via the axis
+    permutation identity[-steps:] + identity[:-steps] (:590-597)."""
+    state = np.asarray(state)
+    n = count_qubits(state)
+    steps = num_steps % n
+    if steps == 0:
+        return to_vector_layout(to_tensor_layout(state), n)
+    identity = list(range(n))
+    return permute_qubits(identity[-steps:] + identity[:-steps], state)
+
+
+def apply_to_qubits(operators, qubits, state):
+    """operations.py:416-503 with fuse_single_qubit_operators (gates/matrix_algebra.py:6-51):
+    operators on the same qubit are multiplied (later operator on the left), then each fused
+    2x2 is applied to its qubit."""
+    fused = {}
+    for q, op in zip(qubits, operators):
+        op = np.asarray(op)
+        fused[q] = np.matmul(op, fused[q]) if q in fused else op
+    out = np.asarray(state)
+    for q, op in fused.items():
+        out = apply_operator(op, [q], out)
+    return out
+
+
+def act_last_qubit(single_qubit_operator, state):
+    """operations.py:189-233: einsum('ab, ...b -> ...a') on the last qubit axis."""
+    state = np.asarray(state)
+    n = count_qubits(state)
+    return apply_operator(np.asarray(single_qubit_operator), [n - 1], state)
+
+
 def multi_cz(qubit_pairs, state_vector):
     """operations.py:657-748 -- sign vector prod_pairs (1 - 2*[(i & crit) == crit]) times the state."""
     state_vector = np.asarray(state_vector)

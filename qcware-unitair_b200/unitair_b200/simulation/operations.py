@@ -6,6 +6,7 @@ reference (cited per function); the work is done by hand-written sm_100a kernels
 the C ABI in include/unitair_b200.h.  Inputs are never modified; outputs are new
 contiguous tensors on the inputs' device and take part in autograd.
 """
+import warnings
 from typing import Iterable, Tuple
 
 import torch
@@ -123,6 +124,43 @@ def act_first_qubits(operator: torch.Tensor, state: torch.Tensor):
     return apply_operator(operator, range(gate_num_qubits), state)
 
 
+def act_first_qubits_tensor(operator: torch.Tensor, state_tensor: torch.Tensor, num_qubits: int,
+                            gate_num_qubits=None):
+    """Tensor-layout variant of act_first_qubits (operations.py:258-329): the operator acts on
+    the first `gate_num_qubits` qubit axes; same three batch structures as apply_operator."""
+    if gate_num_qubits is None:
+        gate_num_qubits = states.count_qubits_gate_matrix(operator)
+    vec = states.to_vector_layout(state_tensor, num_qubits)
+    out = apply_operator(operator, range(gate_num_qubits), vec)
+    return states.to_tensor_layout(out)
+
+
+def act_last_qubit(single_qubit_operator: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+    """Apply a 2x2 operator to the last qubit (operations.py:189-213; deprecated there too)."""
+    warnings.warn(
+        'act_last_qubit and act_last_qubit_tensor are outdated. These\n'
+        'functions will be removed from Unitair in a later release or may\n'
+        'be revised to meet our current standards.\n'
+        'Please consider using apply_operator instead.')
+    num_qubits = states.count_qubits(state)
+    return apply_operator(single_qubit_operator, [num_qubits - 1], state)
+
+
+def act_last_qubit_tensor(single_qubit_operator: torch.Tensor, state_tensor: torch.Tensor) -> torch.Tensor:
+    """Tensor-layout variant of act_last_qubit (operations.py:216-233): contracts the matrix with
+    the last axis, whatever the other axes are."""
+    flat = state_tensor.reshape(-1, 2)
+    if flat.shape[0] == 0:
+        return state_tensor.clone()
+    n = (flat.shape[0].bit_length() - 1) + 1
+    if 1 << (n - 1) != flat.shape[0]:
+        # not a power of two overall: treat the leading axes as a batch of 1-qubit states
+        out = apply_operator(single_qubit_operator, [0], flat)
+    else:
+        out = apply_operator(single_qubit_operator, [n - 1], flat.reshape(-1))
+    return out.reshape(state_tensor.shape)
+
+
 def apply_all_qubits(operator: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
     """Apply the same single-qubit operator to every qubit (operations.py:332-413).
 
@@ -172,6 +210,37 @@ def apply_to_qubits(operators: Iterable[torch.Tensor], qubits: Iterable[int], st
     _lib.require_cuda(state, *ops)
     gates = [([q], op) for q, op in fused.items()]
     return circuit.apply_gates(gates, state)
+
+
+def apply_to_qubits_tensor(operators: Iterable[torch.Tensor], qubits: Iterable[int],
+                           state_tensor: torch.Tensor, num_qubits: int):
+    """Tensor-layout variant of apply_to_qubits (operations.py:449-503)."""
+    vec = states.to_vector_layout(state_tensor, num_qubits)
+    return states.to_tensor_layout(apply_to_qubits(operators, qubits, vec))
+
+
+def permute_qubits_tensor(permutation: Iterable[int], state_tensor: torch.Tensor, num_qubits: int,
+                          contiguous_output: bool = False):
+    """Tensor-layout variant of permute_qubits (operations.py:626-654).  The reference returns a
+    strided view unless contiguous_output=True; here the permutation is one native pass and the
+    result is always contiguous (same values, same shape)."""
+    vec = states.to_vector_layout(state_tensor, num_qubits)
+    return states.to_tensor_layout(permute_qubits(permutation, vec))
+
+
+def swap_tensor(state_tensor: torch.Tensor, qubit_pair: Tuple[int, int], num_qubits: int):
+    """Tensor-layout variant of swap (operations.py:520-537)."""
+    if qubit_pair[0] == qubit_pair[1]:
+        return state_tensor
+    vec = states.to_vector_layout(state_tensor, num_qubits)
+    return states.to_tensor_layout(swap(vec, qubit_pair))
+
+
+def roll_qubits_tensor(state_tensor: torch.Tensor, num_qubits: int, num_steps: int = 1):
+    """Tensor-layout variant of roll_qubits (operations.py:565-597):
+    rolled[a_0, ..., a_{n-1}] = psi[a_k, ..., a_{n-1}, a_0, ..., a_{k-1}]... with k = n - num_steps."""
+    vec = states.to_vector_layout(state_tensor, num_qubits)
+    return states.to_tensor_layout(roll_qubits(vec, num_steps))
 
 
 def permute_qubits(permutation: Iterable[int], state_vector: torch.Tensor):

@@ -339,9 +339,184 @@ def make_diag(arrays, manifest):
     manifest["diag"] = cases
 
 
+def make_layout(arrays, manifest):
+    """Qubit permutations and the tensor-layout fronts (operations.py:189-233, 258-329, 416-654),
+    apply_operator_tensor / apply_all_qubits_tensor (:151-186, :369-413) and the probability
+    vector measure() samples from (measurement.py:41-43)."""
+    from unitair.simulation import operations as ops
+    import warnings
+    gen = torch.Generator().manual_seed(1008)
+    cases = []
+
+    def add(fn, n, batch, arg, st, out, extra=None):
+        key = f"lo{len(cases)}"
+        arrays[key + "_state"] = npy(st)
+        arrays[key + "_out"] = npy(out.contiguous())
+        if extra:
+            for k, v in extra.items():
+                arrays[key + "_" + k] = npy(v)
+        cases.append(dict(key=key, fn=fn, n=n, batch=list(batch), arg=arg))
+
+    for n, batch, steps in [(1, (), 1), (4, (), 1), (4, (), 3), (5, (2,), 2), (6, (), -1), (6, (3, 2), 7),
+                            (7, (), 0), (8, (), 5), (11, (), 4)]:
+        st = rnd_state(gen, n, batch, torch.complex64)
+        add("roll_qubits", n, batch, steps, st, sim.operations.roll_qubits(st, num_steps=steps))
+    for n, batch, steps in [(5, (), 2), (6, (2,), 5)]:
+        st = rnd_state(gen, n, batch, torch.complex128)
+        t = states.to_tensor_layout(st)
+        add("roll_qubits_tensor", n, batch, steps, st, ops.roll_qubits_tensor(t, n, steps))
+    for n, batch, pair in [(5, (), (0, 4)), (6, (3,), (2, 2)), (7, (), (5, 1))]:
+        st = rnd_state(gen, n, batch, torch.complex64)
+        t = states.to_tensor_layout(st)
+        add("swap_tensor", n, batch, list(pair), st, ops.swap_tensor(t, pair, n))
+    for n, batch in [(5, ()), (7, (2,)), (9, ())]:
+        st = rnd_state(gen, n, batch, torch.complex64)
+        perm = torch.randperm(n, generator=gen).tolist()
+        t = states.to_tensor_layout(st)
+        add("permute_qubits_tensor", n, batch, perm, st, ops.permute_qubits_tensor(perm, t, n, contiguous_output=True))
+    for n, k, sb, ob in [(5, 2, (), ()), (6, 3, (3,), ()), (6, 1, (3,), (3,)), (5, 2, (), (4,))]:
+        st = rnd_state(gen, n, sb, torch.complex64)
+        op = rnd_c(gen, tuple(ob) + (2 ** k, 2 ** k), torch.complex64)
+        t = states.to_tensor_layout(st)
+        add("act_first_qubits_tensor", n, sb, k, st, ops.act_first_qubits_tensor(op, t, n, k), {"op": op})
+    for n, k, sb, ob in [(5, 2, (), ()), (6, 3, (2,), ()), (6, 2, (2,), (2,))]:
+        st = rnd_state(gen, n, sb, torch.complex128)
+        op = rnd_c(gen, tuple(ob) + (2 ** k, 2 ** k), torch.complex128)
+        qs = torch.randperm(n, generator=gen)[:k].tolist()
+        t = states.to_tensor_layout(st)
+        add("apply_operator_tensor", n, sb, qs, st, ops.apply_operator_tensor(op, qs, t, n), {"op": op})
+    for n, sb, ob in [(4, (), ()), (6, (3,), ()), (5, (2,), (2,))]:
+        st = rnd_state(gen, n, sb, torch.complex64)
+        op = rnd_c(gen, tuple(ob) + (2, 2), torch.complex64)
+        t = states.to_tensor_layout(st)
+        add("apply_all_qubits_tensor", n, sb, None, st, ops.apply_all_qubits_tensor(op, t, n), {"op": op})
+    for n, sb, ob, qs in [(5, (), (), [0, 3, 3, 1]), (6, (2,), (2,), [5, 0, 5]), (4, (), (), [2]), (7, (3,), (), [6, 1, 0, 1, 6])]:
+        st = rnd_state(gen, n, sb, torch.complex64)
+        oplist = [rnd_c(gen, tuple(ob) + (2, 2), torch.complex64) for _ in qs]
+        out = sim.apply_to_qubits(oplist, qs, st)
+        t = states.to_tensor_layout(st)
+        out_t = ops.apply_to_qubits_tensor(oplist, qs, t, n)
+        assert torch.equal(states.to_vector_layout(out_t.contiguous(), n), out)
+        add("apply_to_qubits", n, sb, qs, st, out, {"ops": torch.stack(oplist)})
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for n, sb in [(1, ()), (4, ()), (6, (3,))]:
+            st = rnd_state(gen, n, sb, torch.complex64)
+            op = rnd_c(gen, (2, 2), torch.complex64)
+            add("act_last_qubit", n, sb, None, st, sim.act_last_qubit(op, st), {"op": op})
+    # the distribution measure() samples from: Categorical(probs=abs_squared(state)).probs
+    for n, dt in [(3, torch.complex64), (8, torch.complex64), (10, torch.complex128)]:
+        st = rnd_c(gen, (2 ** n,), dt, scale=0.7)           # not normalised: Categorical normalises
+        probs = torch.distributions.Categorical(probs=states.abs_squared(st)).probs
+        add("measure_probs", n, (), None, st, probs)
+    manifest["layout"] = cases
+
+
+def seeded_state(seed, n, batch=(), dtype=np.complex64):
+    """numpy-seeded random normalised state: the tests regenerate it instead of storing it."""
+    rng = np.random.default_rng(seed)
+    s = rng.standard_normal(tuple(batch) + (2 ** n,)) + 1j * rng.standard_normal(tuple(batch) + (2 ** n,))
+    s /= np.linalg.norm(s, axis=-1, keepdims=True)
+    return s.astype(dtype)
+
+
+def seeded_haar(rng, dim, dtype):
+    z = rng.standard_normal((dim, dim)) + 1j * rng.standard_normal((dim, dim))
+    q, r = np.linalg.qr(z)
+    d = np.diagonal(r)
+    return (q * (d / np.abs(d))).astype(dtype)
+
+
+def make_fullsize(arrays, manifest):
+    """BASELINE.json's configs at (or near) full size.  Inputs come from numpy seeds (the tests
+    regenerate them); only compact outputs of the reference are stored: sampled amplitudes,
+    per-entry expectation values, the loss and the theta gradient."""
+    torch.set_num_threads(8)
+    out_cases = {}
+    cn = gates.cnot()
+
+    # C2: 24 qubits, 2 layers of the recipe (Haar U(2) on every qubit + Haar U(4) on random pairs)
+    n, layers, seed = 24, 2, 2024
+    rng = np.random.default_rng(seed)
+    psi = torch.from_numpy(seeded_state(seed + 1, n))
+    glist = []
+    for l in range(layers):
+        for q in range(n):
+            u = seeded_haar(rng, 2, np.complex64)
+            glist.append(([q], u))
+        perm = rng.permutation(n).tolist()
+        for j in range(0, n - 1, 2):
+            glist.append(([perm[j], perm[j + 1]], seeded_haar(rng, 4, np.complex64)))
+    for qs, u in glist:
+        psi = sim.apply_operator(torch.from_numpy(u), qs, psi)
+    idx = np.random.default_rng(seed + 2).choice(2 ** n, 4096, replace=False)
+    arrays["c2_idx"] = idx.astype(np.int64)
+    arrays["c2_amps"] = npy(psi)[idx]
+    arrays["c2_norm2"] = npy(states.norm_squared(psi))
+    out_cases["c2"] = dict(n=n, layers=layers, seed=seed, gates=len(glist))
+    del psi
+
+    # C4: 20 qubits complex128, 2 layers of four Haar U(32) blocks on ordered 5-tuples + f64 phase layer
+    n, layers, seed = 20, 2, 4040
+    rng = np.random.default_rng(seed)
+    psi = torch.from_numpy(seeded_state(seed + 1, n, dtype=np.complex128))
+    for l in range(layers):
+        perm = rng.permutation(n).tolist()
+        for j in range(0, n, 5):
+            u = seeded_haar(rng, 32, np.complex128)
+            psi = sim.apply_operator(torch.from_numpy(u), perm[j:j + 5], psi)
+        ang = rng.random(2 ** n) * 2 * np.pi
+        psi = sim.apply_phase(torch.from_numpy(ang), psi)
+    idx = np.random.default_rng(seed + 2).choice(2 ** n, 4096, replace=False)
+    arrays["c4_idx"] = idx.astype(np.int64)
+    arrays["c4_amps"] = npy(psi)[idx]
+    out_cases["c4"] = dict(n=n, layers=layers, seed=seed)
+    del psi
+
+    # C3: 16 qubits, 20 layers (ry, rz on every qubit + CNOT ladder = 940 gates), batch 64, loss =
+    # sum_b <Z_0>, gradient w.r.t. the shared theta by torch autograd through the reference, in
+    # batch chunks of 8 (the tape holds one state per gate)
+    n, B, layers, seed = 16, 64, 20, 3030
+    theta_np = (np.random.default_rng(seed).random((layers, n, 2)) * 2 * np.pi).astype(np.float32)
+    st_np = seeded_state(seed + 1, n, (B,))
+    z0_64 = torch.where((torch.arange(2 ** n) >> (n - 1)) & 1 == 0, 1.0, -1.0).to(torch.float64)
+    # float32 = the reference path under test; float64 (same inputs, promoted) = the yardstick
+    # that says how much of a float32 difference is rounding of an ill-conditioned sum
+    for tag, cdt, rdt in (("", torch.complex64, torch.float32), ("64", torch.complex128, torch.float64)):
+        st = torch.from_numpy(st_np).to(cdt)
+        theta = torch.from_numpy(theta_np).to(rdt).requires_grad_(True)
+        z0 = z0_64.to(rdt)
+        cn = gates.cnot().to(cdt)
+        loss_total = 0.0
+        chunk_grads, ez = [], []
+        for c0 in range(0, B, 8):
+            psi = st[c0:c0 + 8]
+            for l in range(layers):
+                for q in range(n):
+                    psi = sim.apply_operator(gates.exp_y(theta[l, q, 0]).to(cdt), (q,), psi)
+                    psi = sim.apply_operator(gates.exp_z(theta[l, q, 1]).to(cdt), (q,), psi)
+                for q in range(n - 1):
+                    psi = sim.apply_operator(cn, (q, q + 1), psi)
+            e = states.diag_expectation_value(z0, psi)
+            loss = e.sum()
+            g, = torch.autograd.grad(loss, theta)
+            chunk_grads.append(npy(g))
+            loss_total += float(loss.detach())
+            ez.append(npy(e))
+            print("  c3", tag or "32", "chunk", c0, float(loss.detach()), flush=True)
+        arrays["c3_ez" + tag] = np.concatenate(ez)
+        arrays["c3_loss" + tag] = np.float64(loss_total)
+        arrays["c3_gtheta_chunks" + tag] = np.stack(chunk_grads)          # (8, layers, n, 2): per chunk of 8 states
+        arrays["c3_gtheta" + tag] = np.stack(chunk_grads).astype(np.float64).sum(0).astype(npy(theta).dtype)
+    arrays["c3_theta"] = theta_np
+    out_cases["c3"] = dict(n=n, batch=B, layers=layers, seed=seed, chunk=8)
+    manifest["fullsize"] = out_cases
+
+
 ALL = [("apply_operator", make_apply_operator), ("apply_all", make_apply_all),
        ("phase", make_phase), ("reductions", make_reductions),
-       ("grads", make_grads), ("circuits", make_circuits), ("diag", make_diag)]
+       ("grads", make_grads), ("circuits", make_circuits), ("diag", make_diag),
+       ("layout", make_layout), ("fullsize", make_fullsize)]
 
 
 def main():

@@ -158,3 +158,43 @@ def test_oracle_sampling_distribution_matches_reference_probabilities():
     assert set(orc.sample_indices(e3, rng.random(50)).tolist()) == {3}
     assert orc.sample_indices(st, [0.0])[0] == 0
     assert orc.sample_indices(st, [1.0 - 1e-16])[0] == 2 ** n - 1
+
+
+def test_layout_golden(golden):
+    """Qubit permutations, tensor-layout fronts, apply_to_qubits, act_last_qubit and the measure()
+    probability vector, all produced by the unmodified reference (make_golden.py: make_layout)."""
+    arr = golden.arrays("layout")
+    seen = set()
+    for c in golden.manifest["layout"]:
+        k, fn, n = c["key"], c["fn"], c["n"]
+        st, ref = arr[k + "_state"], arr[k + "_out"]
+        seen.add(fn)
+        flat = ref.reshape(st.shape) if ref.size == st.size and fn != "measure_probs" else ref
+        if fn in ("roll_qubits", "roll_qubits_tensor"):
+            out = orc.roll_qubits(st, c["arg"])
+            assert np.array_equal(out, flat), c
+        elif fn == "swap_tensor":
+            assert np.array_equal(orc.swap(st, tuple(c["arg"])), flat), c
+        elif fn == "permute_qubits_tensor":
+            assert np.array_equal(orc.permute_qubits(c["arg"], st), flat), c
+        elif fn == "act_first_qubits_tensor":
+            out = orc.apply_operator(arr[k + "_op"], list(range(c["arg"])), st)
+            assert_close(out, ref.reshape(out.shape), ref.dtype, what=str(c))
+        elif fn == "apply_operator_tensor":
+            out = orc.apply_operator(arr[k + "_op"], c["arg"], st)
+            assert_close(out, ref.reshape(out.shape), ref.dtype, what=str(c))
+        elif fn == "apply_all_qubits_tensor":
+            out = orc.apply_all_qubits(arr[k + "_op"], st)
+            assert_close(out, ref.reshape(out.shape), ref.dtype, factor=3, what=str(c))
+        elif fn == "apply_to_qubits":
+            out = orc.apply_to_qubits(list(arr[k + "_ops"]), c["arg"], st)
+            assert_close(out, flat, ref.dtype, factor=3, what=str(c))
+        elif fn == "act_last_qubit":
+            assert_close(orc.act_last_qubit(arr[k + "_op"], st), flat, ref.dtype, what=str(c))
+        elif fn == "measure_probs":
+            p = orc.measurement_probabilities(st)
+            assert p.shape == ref.shape
+            assert np.allclose(p, ref, rtol=(1e-5 if st.dtype == np.complex64 else 1e-12), atol=0), c
+    assert seen == {"roll_qubits", "roll_qubits_tensor", "swap_tensor", "permute_qubits_tensor",
+                    "act_first_qubits_tensor", "apply_operator_tensor", "apply_all_qubits_tensor",
+                    "apply_to_qubits", "act_last_qubit", "measure_probs"}
