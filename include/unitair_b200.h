@@ -114,6 +114,17 @@ int ua_inner_product(int dtype, void *out_complex, const void *a, const void *b,
                      long long b_batch_stride,
                      void *workspace, size_t workspace_bytes, void *stream);
 
+/* Backward of abs_squared / norm_squared / diag_expectation_value w.r.t. the state in one pass
+ * (autograd of src/unitair/states/innerprod.py:26,46,59; the eager formula 2*g*d*psi costs three
+ * kernels and two full-size temporaries):
+ *   out[b,e] = scale * g[b*g_batch_stride + e*g_elem_stride] * (diag ? diag[b*diag_batch_stride + e] : 1)
+ *              * in[b*in_batch_stride + e]
+ * g / diag are real (f32 for UA_C64, f64 for UA_C128); strides are 0 or the natural ones.        */
+int ua_real_scale(int dtype, void *out, const void *in, const void *g_real, const void *diag_real,
+                  long long elems, long long batch, long long in_batch_stride,
+                  long long g_batch_stride, long long g_elem_stride, long long diag_batch_stride,
+                  double scale, void *stream);
+
 /* Fused shared-memory pass: a list of dense gates (k <= 3 each) whose target bits all
  * lie inside one tile = the low `tile_low_bits` index bits plus `num_high` chosen higher
  * bit positions.  Every tile is staged once in shared memory, all gates are applied

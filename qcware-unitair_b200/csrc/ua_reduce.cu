@@ -151,6 +151,39 @@ __global__ void __launch_bounds__(256) abs2_vec_kernel(float2 *__restrict__ out,
             __stcs(out + i0 + u * 256, make_float2(x[u].x * x[u].x + x[u].y * x[u].y, x[u].z * x[u].z + x[u].w * x[u].w));
 }
 
+
+// Backward of the real-valued reductions in ONE pass (no temporaries):
+//   out[b, e] = scale * g[b*gbs + e*ges] * (diag ? diag[b*dbs + e] : 1) * in[b*ibs + e]
+// abs_squared: g per amplitude; norm_squared / diag_expectation_value: g per row (ges = 0).
+// (PyTorch's convention for a real loss: d|z|^2 -> 2 g z.)
+template <typename R>
+__global__ void __launch_bounds__(256) real_scale_kernel(typename CplxOf<R>::type *__restrict__ out,
+                                                        const typename CplxOf<R>::type *__restrict__ in,
+                                                        const R *__restrict__ g, const R *__restrict__ diag,
+                                                        long long elems, long long batch, long long ibs,
+                                                        long long gbs, long long ges, long long dbs, R scale) {
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    const long long vec_per_row = elems / APV;
+    const long long total = vec_per_row * batch;
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long b = i / vec_per_row, v = i - b * vec_per_row;
+        const long long e = v * APV;
+        const V x = ld16<true>(reinterpret_cast<const V *>(in + b * ibs + e));
+        R f0 = scale * g[b * gbs + e * ges];
+        if (diag) f0 *= diag[b * dbs + e];
+        V y;
+        if constexpr (APV == 2) {
+            R f1 = scale * g[b * gbs + (e + 1) * ges];
+            if (diag) f1 *= diag[b * dbs + e + 1];
+            y = make_float4(f0 * x.x, f0 * x.y, f1 * x.z, f1 * x.w);
+        } else {
+            y = make_double2(f0 * x.x, f0 * x.y);
+        }
+        st16<true>(reinterpret_cast<V *>(out + b * elems + e), y);
+    }
+}
+
 }  // namespace ua
 
 using namespace ua;
@@ -222,4 +255,32 @@ extern "C" int ua_inner_product(int dtype, void *out_complex, const void *a, con
     if (dtype == UA_C64) return run_reduce<float, OP_INNER>(r, batch, workspace, workspace_bytes, st, "ua_inner_product");
     if (dtype == UA_C128) return run_reduce<double, OP_INNER>(r, batch, workspace, workspace_bytes, st, "ua_inner_product");
     set_error("ua_inner_product: bad dtype"); return UA_ERR_INVALID;
+}
+
+extern "C" int ua_real_scale(int dtype, void *out, const void *in, const void *g_real, const void *diag_real,
+                             long long elems, long long batch, long long in_batch_stride,
+                             long long g_batch_stride, long long g_elem_stride, long long diag_batch_stride,
+                             double scale, void *stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (!out || !in || !g_real || elems < 1 || batch < 1) { set_error("ua_real_scale: bad arguments"); return UA_ERR_INVALID; }
+    if ((in_batch_stride != 0 && in_batch_stride != elems) || (diag_batch_stride != 0 && diag_batch_stride != elems) ||
+        (g_elem_stride != 0 && g_elem_stride != 1)) {
+        set_error("ua_real_scale: unsupported strides"); return UA_ERR_INVALID;
+    }
+    if ((((uintptr_t)out | (uintptr_t)in) & 15) || (dtype == UA_C64 && (elems & 1))) {
+        set_error("ua_real_scale: pointers must be 16-byte aligned (complex64 rows of even length)"); return UA_ERR_UNSUPPORTED;
+    }
+    const long long vecs = (dtype == UA_C64 ? elems / 2 : elems) * batch;
+    long long blocks = (vecs + 255) / 256;
+    { const long long cap = (long long)sm_count() * 32; if (blocks > cap) blocks = cap; }
+    if (dtype == UA_C64)
+        real_scale_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<float2 *>(out), reinterpret_cast<const float2 *>(in),
+            reinterpret_cast<const float *>(g_real), reinterpret_cast<const float *>(diag_real), elems, batch, in_batch_stride,
+            g_batch_stride, g_elem_stride, diag_batch_stride, (float)scale);
+    else if (dtype == UA_C128)
+        real_scale_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<double2 *>(out), reinterpret_cast<const double2 *>(in),
+            reinterpret_cast<const double *>(g_real), reinterpret_cast<const double *>(diag_real), elems, batch, in_batch_stride,
+            g_batch_stride, g_elem_stride, diag_batch_stride, scale);
+    else { set_error("ua_real_scale: bad dtype"); return UA_ERR_INVALID; }
+    return check_launch("real_scale_kernel");
 }

@@ -14,6 +14,8 @@ from . import gates
 from . import initializations
 from . import circuit
 from . import hoststream
+from . import batch
+from .batch import shard_batch, all_reduce_gradients
 from .hoststream import HostCircuitStream
 
 from .states.shapes import StateLayout

@@ -70,6 +70,8 @@ def _declare(L):
                                       c_longlong, c_longlong, c_void_p, c_size_t, c_void_p]
     L.ua_inner_product.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong,
                                    c_longlong, c_longlong, c_void_p, c_size_t, c_void_p]
+    L.ua_real_scale.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_longlong, c_longlong,
+                                c_longlong, c_longlong, c_longlong, ctypes.c_double, c_void_p]
     L.ua_fused_limits.argtypes = [c_int, p_int, p_int]
     L.ua_apply_fused_pass.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                       p_int, c_int, p_int, p_int, p_ll, c_void_p, c_longlong,
@@ -96,7 +98,7 @@ def _declare(L):
                                       POINTER(c_ulonglong), c_void_p]
     for name in ("ua_apply_sign_masks", "ua_apply_gate", "ua_gate_grad", "ua_apply_phase", "ua_phase_backward",
                  "ua_abs_squared", "ua_norm_squared", "ua_diag_expectation", "ua_inner_product",
-                 "ua_fused_limits", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits",
+                 "ua_fused_limits", "ua_real_scale", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits",
                  "ua_apply_fused_pass_scatter", "ua_apply_fused_pass_hostmats",
                  "ua_apply_fused_pass_scatter_hostmats", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close",
                  "ua_sample_block_sums", "ua_sample_locate"):

@@ -29,6 +29,26 @@ def _contig(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _real_scale(state, g, diag, batch, elems, s_bs, g_bs, g_es, d_bs, scale=2.0):
+    """scale * g * diag * state in one native pass (ua_real_scale), or None when the layout does
+    not fit it (odd complex64 rows, misaligned views): the caller then uses the eager formula."""
+    if state.numel() == 0 or (state.dtype == torch.complex64 and elems % 2):
+        return None
+    g = _contig(g.to(_real_dtype(state.dtype)))
+    out = torch.empty((batch, elems), dtype=state.dtype, device=state.device)
+    if (state.data_ptr() | out.data_ptr()) & 15:
+        return None
+    dev = state.device
+    with L.on_device(dev):
+        rc = L.lib().ua_real_scale(L.dtype_code(state.dtype), out.data_ptr(), state.data_ptr(), g.data_ptr(),
+                                   diag.data_ptr() if diag is not None else None, elems, batch, s_bs,
+                                   g_bs, g_es, d_bs, float(scale), L.stream_ptr(dev))
+    if rc == L.UA_ERR_UNSUPPORTED:
+        return None
+    L.check(rc)
+    return out
+
+
 class _AbsSquared(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state):
@@ -45,7 +65,10 @@ class _AbsSquared(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad):
         state, = ctx.saved_tensors
-        return 2 * grad * state        # d|z|^2 -> 2 g z (conjugate Wirtinger convention)
+        # d|z|^2 -> 2 g z (conjugate Wirtinger convention), one fused pass
+        n = state.numel()
+        out = _real_scale(state, _contig(grad), None, 1, n, n, n, 1, 0)
+        return out.reshape(state.shape) if out is not None else 2 * grad * state
 
 
 def abs_squared(state: torch.Tensor):
@@ -84,7 +107,9 @@ class _NormSquared(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad):
         state, = ctx.saved_tensors
-        return 2 * grad.unsqueeze(-1) * state
+        batch, elems = _rows(state)
+        out = _real_scale(state, grad.reshape(-1), None, batch, elems, elems, 1, 0, 0) if batch else None
+        return out.reshape(state.shape) if out is not None else 2 * grad.unsqueeze(-1) * state
 
 
 def norm_squared(state: torch.Tensor):
@@ -121,10 +146,16 @@ class _DiagExpectation(torch.autograd.Function):
         s2 = state.reshape(-1, elems)
         g_state = g_diag = None
         if ctx.needs_input_grad[1]:
-            g_state = 2 * g * d2 * s2                       # (batch, elems)
-            if s_bs == 0 and batch > 1:
-                g_state = g_state.sum(0, keepdim=True)
-            g_state = g_state.reshape(state.shape)
+            fused = None
+            if not (s_bs == 0 and batch > 1):               # a broadcast state needs a sum over the batch
+                fused = _real_scale(state, grad.reshape(-1), diag, batch, elems, s_bs, 1, 0, d_bs)
+            if fused is not None:
+                g_state = fused.reshape(state.shape)
+            else:
+                g_state = 2 * g * d2 * s2                       # (batch, elems)
+                if s_bs == 0 and batch > 1:
+                    g_state = g_state.sum(0, keepdim=True)
+                g_state = g_state.reshape(state.shape)
         if ctx.needs_input_grad[0]:
             g_diag = g * (s2.real ** 2 + s2.imag ** 2)
             if d_bs == 0 and batch > 1:
