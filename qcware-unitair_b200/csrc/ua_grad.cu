@@ -126,6 +126,143 @@ __global__ void __launch_bounds__(256) gate_grad_kernel(const GradArgs a) {
     }
 }
 
+
+// Register variant for 1- and 2-qubit gates (the ones training circuits are made of).  Every
+// thread walks complete amplitude groups of grad_out and psi_in with 16-byte streaming loads (a
+// complex64 vector carries two independent groups unless a target is index bit 0), forms the
+// D x D outer product in fp32 registers over CH groups, folds the chunk into fp64 accumulators,
+// and the block reduces them with warp shuffles: no shared-memory staging, 16 B / 32 B of HBM
+// traffic per amplitude at streaming rate.
+template <typename R, int K, bool LOW>
+__global__ void __launch_bounds__(256, 2) gate_grad_reg_kernel(const GradArgs a) {
+    using C = typename CplxOf<R>::type;
+    using V = typename VecOf<R>::type;
+    constexpr int APV = VecOf<R>::APV;
+    constexpr int APVLOG = APV == 2 ? 1 : 0;
+    constexpr int D = 1 << K;
+    constexpr int E = D * D;
+    constexpr int KH = LOW ? K - 1 : K;             // vector-level target bits
+    constexpr int NV = 1 << KH;                     // vectors per group
+    constexpr int NG = (APV == 2 && !LOW) ? 2 : 1;  // independent groups per vector set
+    constexpr int CH = NV >= 2 ? 4 : 8;             // vector sets per fp32 chunk (>= 8 loads in flight)
+    __shared__ double2 sRed[8][E];
+
+    const long long seg = blockIdx.x / a.bps;
+    const int blk = blockIdx.x - (int)(seg * a.bps);
+    // vector-level positions of the targets, ascending; gate-order row of every member
+    int vb[KH > 0 ? KH : 1];
+#pragma unroll
+    for (int i = 0; i < KH; ++i) vb[i] = a.spos[i + (LOW ? 1 : 0)] - APVLOG;
+    int row_of[D];                                   // member (sorted-bit order) -> gate-order row index
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        int r = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            // sorted target i has bit position spos[i]; find its place j in gate order
+#pragma unroll
+            for (int j = 0; j < K; ++j)
+                if (a.pos[j] == a.spos[i] && ((m >> i) & 1)) r |= 1 << (K - 1 - j);
+        }
+        row_of[m] = r;
+    }
+    const int nbits = 63 - __clzll((unsigned long long)a.dim);        // n
+    const long long sets_per_state = a.dim >> (K + (LOW ? 0 : APVLOG));   // vector sets per state row
+    const long long sets = a.per_batch ? sets_per_state : sets_per_state * a.tiles_per_seg;   // tiles_per_seg = batch here
+    const V *__restrict__ gv = reinterpret_cast<const V *>(a.g);
+    const V *__restrict__ pv = reinterpret_cast<const V *>(a.psi);
+
+    double2 acc[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] = make_double2(0.0, 0.0);
+
+    const long long stride = (long long)a.bps * 256;
+    for (long long i0 = (long long)blk * 256 + threadIdx.x; i0 < sets; i0 += stride * CH) {
+        // complex128 accumulates straight into the fp64 registers (no fp32 chunk to fold)
+        constexpr bool CHUNK = sizeof(R) == 4;
+        R px[CHUNK ? E : 1], py[CHUNK ? E : 1];
+        if constexpr (CHUNK) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) { px[e] = R(0); py[e] = R(0); }
+        }
+#pragma unroll
+        for (int u = 0; u < CH; ++u) {
+            const long long i = i0 + u * stride;
+            if (i >= sets) break;
+            long long b, s;
+            if (a.per_batch) { b = seg; s = i; }
+            else { b = i / sets_per_state; s = i - b * sets_per_state; }
+            uint64_t base = (uint64_t)s;
+#pragma unroll
+            for (int j = 0; j < KH; ++j) base = insert_zero(base, vb[j]);
+            const uint64_t gofs = ((uint64_t)b << (nbits - APVLOG)) + base;
+            const uint64_t pofs = (uint64_t)b * (uint64_t)(a.psi_bstride >> APVLOG) + base;
+            V g[NV], p[NV];
+#pragma unroll
+            for (int c = 0; c < NV; ++c) {
+                uint64_t o = 0;
+#pragma unroll
+                for (int j = 0; j < KH; ++j)
+                    if ((c >> j) & 1) o |= 1ull << vb[j];
+                g[c] = ld16<true>(gv + gofs + o);
+                p[c] = ld16<true>(pv + pofs + o);
+            }
+#pragma unroll
+            for (int h = 0; h < NG; ++h) {
+                C gm[D], pm[D];                      // members in sorted-bit order
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    if constexpr (APV == 1) { gm[m] = g[m]; pm[m] = p[m]; }
+                    else if constexpr (LOW) {
+                        gm[m] = (m & 1) ? mk(g[m >> 1].z, g[m >> 1].w) : mk(g[m >> 1].x, g[m >> 1].y);
+                        pm[m] = (m & 1) ? mk(p[m >> 1].z, p[m >> 1].w) : mk(p[m >> 1].x, p[m >> 1].y);
+                    } else {
+                        gm[m] = h ? mk(g[m].z, g[m].w) : mk(g[m].x, g[m].y);
+                        pm[m] = h ? mk(p[m].z, p[m].w) : mk(p[m].x, p[m].y);
+                    }
+                }
+#pragma unroll
+                for (int ma = 0; ma < D; ++ma)
+#pragma unroll
+                    for (int mb = 0; mb < D; ++mb) {
+                        const int e = ma * D + mb;   // sorted order; mapped to gate order at the end
+                        if constexpr (CHUNK) {
+                            px[e] = fma(gm[ma].x, pm[mb].x, px[e]); px[e] = fma(gm[ma].y, pm[mb].y, px[e]);
+                            py[e] = fma(gm[ma].y, pm[mb].x, py[e]); py[e] = fma(-gm[ma].x, pm[mb].y, py[e]);
+                        } else {
+                            acc[e].x = fma(gm[ma].x, pm[mb].x, acc[e].x); acc[e].x = fma(gm[ma].y, pm[mb].y, acc[e].x);
+                            acc[e].y = fma(gm[ma].y, pm[mb].x, acc[e].y); acc[e].y = fma(-gm[ma].x, pm[mb].y, acc[e].y);
+                        }
+                    }
+            }
+        }
+        if constexpr (CHUNK) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) { acc[e].x += (double)px[e]; acc[e].y += (double)py[e]; }
+        }
+    }
+    // block reduction: shuffles inside the warp, shared memory across the 8 warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        double x = acc[e].x, y = acc[e].y;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            x += __shfl_xor_sync(0xffffffffu, x, o);
+            y += __shfl_xor_sync(0xffffffffu, y, o);
+        }
+        if (lane == 0) sRed[warp][e] = make_double2(x, y);
+    }
+    __syncthreads();
+    if (threadIdx.x < E) {
+        double2 t = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { t.x += sRed[w][threadIdx.x].x; t.y += sRed[w][threadIdx.x].y; }
+        const int ma = threadIdx.x / D, mb = threadIdx.x % D;
+        a.partial[((long long)seg * a.bps + blk) * E + row_of[ma] * D + row_of[mb]] = t;
+    }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256) gate_grad_final_kernel(void *out, const double2 *partial, int bps, int E) {
     using C = typename CplxOf<R>::type;
@@ -142,8 +279,26 @@ __global__ void __launch_bounds__(256) gate_grad_final_kernel(void *out, const d
 
 struct GradPlan { long long nseg, tiles_per_state, tiles_per_seg; int bps; };
 
+static bool grad_reg_path(int dtype, int n, int k) {
+    // the register kernel needs at least one whole vector set per state row
+    return k <= 2 && n >= k + (dtype == UA_C64 ? 1 : 0);
+}
+
 static GradPlan plan_grad(int dtype, int n, int k, long long batch, long long gate_bstride) {
     GradPlan p;
+    if (grad_reg_path(dtype, n, k)) {
+        const bool per_batch = gate_bstride != 0;
+        p.nseg = per_batch ? batch : 1;
+        p.tiles_per_state = 0;
+        p.tiles_per_seg = batch;                       // register kernel: the batch size
+        const long long sets = ((1ll << n) >> (k + (dtype == UA_C64 ? 1 : 0))) * (per_batch ? 1 : batch);
+        long long want = ((long long)sm_count() * 2) / p.nseg;     // 2 CTAs per SM
+        const long long most = (sets + 256 * 4 - 1) / (256 * 4);
+        if (want > most) want = most;
+        if (want < 1) want = 1;
+        p.bps = (int)want;
+        return p;
+    }
     const int tile_elems = (dtype == UA_C64) ? 2048 : 1024;
     const long long tr = tile_elems >> k;
     const long long cols = 1ll << (n - k);
@@ -216,7 +371,25 @@ extern "C" int ua_gate_grad(int dtype, void *grad_gate, const void *grad_out, co
     a.cols_per_state = 1ll << (n - k);
     const long long grid = p.nseg * p.bps;
     if (grid > 0x7fffffffll) { set_error("ua_gate_grad: grid too large"); return UA_ERR_UNSUPPORTED; }
-    int rc = (dtype == UA_C64) ? launch_grad<float>(k, a, (unsigned)grid, st) : launch_grad<double>(k, a, (unsigned)grid, st);
+    int rc;
+    if (grad_reg_path(dtype, n, k)) {
+        const bool low = dtype == UA_C64 && a.spos[0] == 0;
+        const bool aligned = !(((uintptr_t)grad_out | (uintptr_t)psi_in) & 15);
+        if (!aligned) { set_error("ua_gate_grad: pointers must be 16-byte aligned"); return UA_ERR_INVALID; }
+        const unsigned gr = (unsigned)grid;
+        if (dtype == UA_C64) {
+            if (k == 1 && low) gate_grad_reg_kernel<float, 1, true><<<gr, 256, 0, st>>>(a);
+            else if (k == 1) gate_grad_reg_kernel<float, 1, false><<<gr, 256, 0, st>>>(a);
+            else if (low) gate_grad_reg_kernel<float, 2, true><<<gr, 256, 0, st>>>(a);
+            else gate_grad_reg_kernel<float, 2, false><<<gr, 256, 0, st>>>(a);
+        } else {
+            if (k == 1) gate_grad_reg_kernel<double, 1, false><<<gr, 256, 0, st>>>(a);
+            else gate_grad_reg_kernel<double, 2, false><<<gr, 256, 0, st>>>(a);
+        }
+        rc = check_launch("gate_grad_reg_kernel");
+    } else {
+        rc = (dtype == UA_C64) ? launch_grad<float>(k, a, (unsigned)grid, st) : launch_grad<double>(k, a, (unsigned)grid, st);
+    }
     if (rc) return rc;
     const int E = 1 << (2 * k);
     if (dtype == UA_C64) gate_grad_final_kernel<float><<<(unsigned)p.nseg, 256, 0, st>>>(grad_gate, a.partial, p.bps, E);
