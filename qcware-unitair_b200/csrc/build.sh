@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-r
        -Xcompiler -fPIC ${UA_NVCC_EXTRA:-})
 objs=()
 pids=()
-for f in ua_api ua_gate ua_phase ua_reduce ua_grad ua_tile ua_cluster ua_permute ua_diag ua_sample; do
+for f in ua_api ua_gate ua_phase ua_reduce ua_grad ua_tile ua_cluster ua_tc5 ua_permute ua_diag ua_sample; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/$f.o" &
   pids+=($!)
   objs+=("$HERE/$f.o")

@@ -16,6 +16,9 @@
 
 namespace ua {
 
+int launch_gate_tc5(void *out, const void *in, const void *gate, int total_bits, long long batch, const int *spos,
+                    const int *gbit, int adjoint, cudaStream_t st);      // ua_tc5.cu
+
 struct GateArgs {
     const void *in;
     void *out;
@@ -452,6 +455,19 @@ extern "C" int ua_apply_gate(int dtype, void *out, const void *in, const void *g
             if (k == 4) gate_dmma_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(d);
             else gate_dmma_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(d);
             return check_launch("gate_dmma_kernel");
+        }
+    }
+
+    // complex64 dense 5-qubit blocks with a shared gate: tcgen05 tensor cores (3xTF32), ua_tc5.cu
+    {
+        static int use_tc = -1;
+        if (use_tc < 0) { const char *e = getenv("UA_TC5"); use_tc = e ? atoi(e) : 1; }
+        const bool flat_c64 = dtype == UA_C64 && gate_batch_stride == 0 && (in_batch_stride == dim || batch == 1);
+        if (use_tc && flat_c64 && k == 5) {
+            int sp[5], gb[5];
+            for (int i = 0; i < 5; ++i) { sp[i] = pos[order[i]]; gb[i] = k - 1 - order[i]; }
+            const int rc = launch_gate_tc5(out, in, gate, n, batch, sp, gb, adjoint ? 1 : 0, st);
+            if (rc != UA_ERR_UNSUPPORTED) return rc;      // shapes it does not cover fall through to the CUDA cores
         }
     }
 
