@@ -37,6 +37,11 @@ def main():
         half.run(st)
         spread = float(st.local[0].abs()) if rank == 0 else 0.0       # the circuit must move the state
         nrm_mid = float(st.norm_squared())
+        st.release_peers()
+        st.local = st.spare = None           # 36 qubits on 8 GPUs: 64 GiB + 64 GiB spare per state
+        del half
+        torch.cuda.empty_cache()
+        dist.barrier()
         st2 = sharded.ShardedState.zero_state(n, torch.complex64, dev)
         sc.run(st2)
         nrm = float(st2.norm_squared())
@@ -51,10 +56,11 @@ def main():
             assert rest < 1e-7, rest
             print(f"OK inverse mode={mode} world={world} n={n} swaps={sc.num_swaps} "
                   f"fused_swaps={sc.num_fused_swaps} |psi-e0|^2={rest:.2e}")
-        st.release_peers()
         st2.release_peers()
-        del st, st2, sc, half
+        st2.local = st2.spare = None
+        del st, st2, sc
         torch.cuda.empty_cache()
+        dist.barrier()
         # ---- GHZ: H on qubit 0, CNOT(q, q+1) chain ------------------------------------------
         h = ua.gates.hadamard(device=dev, dtype=torch.complex64)
         cn = ua.gates.cnot(device=dev, dtype=torch.complex64)
@@ -72,8 +78,10 @@ def main():
             assert abs(nrm - 1) < 1e-5, nrm
             print(f"OK ghz mode={mode} world={world} n={n}")
         st.release_peers()
+        st.local = st.spare = None
         del st
         torch.cuda.empty_cache()
+        dist.barrier()
     dist.destroy_process_group()
 
 
