@@ -16,7 +16,7 @@ from . import circuit
 from . import hoststream
 from . import batch
 from .batch import shard_batch, all_reduce_gradients
-from .hoststream import HostCircuitStream
+from .hoststream import HostCircuitStream, ShardedHostStream
 
 from .states.shapes import StateLayout
 from .initializations import unit_vector, uniform_superposition, rand_state

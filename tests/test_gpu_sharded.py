@@ -21,6 +21,7 @@ def test_sharded_matches_single_gpu(world):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("OK dtype") == 4, out.stdout[-2000:]
+    assert "OK host stream" in out.stdout, out.stdout[-2000:]
 
 
 @pytest.mark.parametrize("world,total_qubits,layers", [(2, 26, 3), (8, 33, 2), (8, 36, 2)])
