@@ -738,10 +738,11 @@ class ScatterTail:
                 ev.record(cur)
                 if spans is not None and k == 0:
                     first = ev
-                cs = copy_streams[k % len(copy_streams)]
-                cs.wait_event(ev)
-                csp = cs.cuda_stream
-                for b in order:
+                # the blocks of a slice are spread over the copy streams (two copy engines at work)
+                for cs in copy_streams:
+                    cs.wait_event(ev)
+                for i, b in enumerate(order):
+                    csp = copy_streams[i % len(copy_streams)].cuda_stream
                     L.check(lib.ua_peer_copy(dst_ptrs[b] + k * sub, stage_ptr + b * block_bytes + k * sub, sub, csp))
             if mark is not None:
                 mark("gates")
