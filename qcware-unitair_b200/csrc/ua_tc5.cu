@@ -31,7 +31,11 @@ namespace ua {
 // against 3.7-4.4 ms per 30-qubit pass): the pass is bound by the serial chain of a CTA, not by
 // the length of the DRAM runs, so more resident CTAs win.
 // L2 prefetch of tiles further ahead (cp.async.bulk.prefetch.tensor) was measured and lost:
-// 4.7-5.6 ms per 30-qubit pass against 3.6-4.2 ms without (profiles/r02_tc5_variants.txt)
+// 4.7-5.6 ms per 30-qubit pass against 3.6-4.2 ms without.  So did a ring version (one CTA per SM,
+// producer warp + 3-4 teams of 128 threads on a ring of 8-9 tile buffers, the structure of
+// cluster_ring_kernel): 5.3-8.2 ms, 4.8-7.5 ms with the tensor-core work switched off -- with
+// 16 KiB tiles made of 512-byte runs one producer warp per SM cannot issue the copies fast enough,
+// three CTAs with their own issuing warps can (profiles/r02_tc5_variants.txt).
 constexpr int TC_AHEAD = 0;
 constexpr int TC_PASS = 2;
 constexpr int TC_HALVES = 1 << (TC_PASS - 2);
@@ -240,8 +244,10 @@ __global__ void __launch_bounds__(TC_THREADS, TC_PASS == 2 ? 3 : 2) gate_tc5_ker
             issue_copies(tile_index(tile_id + gridDim.x), 0, buf ^ 1);
             // ... and pull a tile further ahead into L2: the two 16 KiB buffers alone keep too few
             // bytes in flight per SM to cover the HBM latency
-            const long long tp = tile_id + (long long)(1 + TC_AHEAD) * gridDim.x;
-            if (tp < a.num_tiles) issue_copies(tile_index(tp), 2, 0);
+            if (TC_AHEAD > 0) {
+                const long long tp = tile_id + (long long)(1 + TC_AHEAD) * gridDim.x;
+                if (tp < a.num_tiles) issue_copies(tile_index(tp), 2, 0);
+            }
         }
         mbar_wait(smem_u32(&bar_mma), it & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;");
