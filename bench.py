@@ -586,14 +586,7 @@ def run_ours(args):
         tplan.run(sstate, timing=tm)
         line["phase_ms_per_step_rank0"] = {k: round(v, 2) for k, v in tm.items()}
         nv = None
-        if tplan.p2p and tm.get("copy_span"):
-            # pipelined exchanges: copy-engine transfers of finished slices; the span runs from the
-            # first slice being ready to the last one delivered (waits for later slices included)
-            nv = tm["copy_bytes"] / (tm["copy_span"] / 1e3) / 1e9
-            what = ("copy-engine transfers of the pipelined exchanges, first slice ready -> last slice "
-                    "delivered (waits for the gate work of later slices included)")
-            line["exchange"] = "p2p, pipelined (last passes of an epoch run slice by slice; copy engines send finished slices to the peers)"
-        elif tplan.p2p and tm.get("scatter_pass"):
+        if tplan.p2p and tm.get("scatter_pass"):
             # the passes whose stores cross NVLink: bytes leaving this GPU / their device time
             nv = tplan.swap_bytes_per_step / (tm["scatter_pass"] / 1e3) / 1e9
             what = "peer stores of the fused scatter passes (compute included in the pass time)"

@@ -185,31 +185,6 @@ int ua_apply_fused_pass_scatter_hostmats(int dtype, const void *in, long long to
                                          const long long *host_gate_offset, const void *host_gate_mats,
                                          int num_scatter_bits, const int *host_scatter_pos,
                                          void *const *host_dst_ptrs, int visit_xor, void *stream);
-/* The same two passes restricted to a 2^-c slice of the state: only the amplitudes whose index
- * bits host_chunk_bits[] (c <= UA_MAX_CHUNK_BITS, ascending, >= tile_low_bits, none of them a tile
- * bit or a scatter bit) have the value chunk_index (bit i of chunk_index <-> host_chunk_bits[i])
- * are read and written.  A run of passes whose tiles all avoid the chunk bits can then be
- * executed slice by slice, and the copy of a finished slice to the peer GPUs (ua_peer_copy on
- * another stream, copy engines) overlaps the gate work of the next slices: the pipelined
- * global-qubit exchange of unitair_b200/sharded.py.  Nothing in the reference corresponds
- * (single device).                                                                            */
-#define UA_MAX_CHUNK_BITS 3
-int ua_apply_fused_pass_hostmats_chunk(int dtype, void *out, const void *in, long long total_amps,
-                                       int total_bits, int tile_low_bits, int num_high,
-                                       const int *host_high_pos, int num_gates, const int *host_gate_k,
-                                       const int *host_gate_bits, const long long *host_gate_offset,
-                                       const void *host_gate_mats, int adjoint, int num_chunk_bits,
-                                       const int *host_chunk_bits, int chunk_index, void *stream);
-int ua_apply_fused_pass_scatter_hostmats_chunk(int dtype, const void *in, long long total_amps, int total_bits,
-                                               int tile_low_bits, int num_high, const int *host_high_pos,
-                                               int num_gates, const int *host_gate_k, const int *host_gate_bits,
-                                               const long long *host_gate_offset, const void *host_gate_mats,
-                                               int num_scatter_bits, const int *host_scatter_pos,
-                                               void *const *host_dst_ptrs, int visit_xor, int num_chunk_bits,
-                                               const int *host_chunk_bits, int chunk_index, void *stream);
-/* Asynchronous device-to-device copy on `stream` (copy engines); dst and/or src may be peer
- * memory mapped with ua_ipc_open.                                                              */
-int ua_peer_copy(void *dst, const void *src, long long bytes, void *stream);
 
 /* Peer memory for the scatter pass: export a device allocation of this process / map one of
  * another process on the same node (CUDA IPC).  ua_ipc_export writes a 64-byte handle for the

@@ -96,16 +96,3 @@ extern "C" int ua_ipc_close(void *ptr, long long offset) {
     }
     return UA_OK;
 }
-
-extern "C" int ua_peer_copy(void *dst, const void *src, long long bytes, void *stream) {
-    using namespace ua;
-    if (!dst || !src || bytes < 0) { set_error("ua_peer_copy: bad argument"); return UA_ERR_INVALID; }
-    if (bytes == 0) return UA_OK;
-    const cudaError_t e = cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, reinterpret_cast<cudaStream_t>(stream));
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        set_error("ua_peer_copy: %s", cudaGetErrorString(e));
-        return UA_ERR_CUDA;
-    }
-    return UA_OK;
-}

@@ -54,9 +54,6 @@ struct ClusterGeom {
     int tab_front, tab_bytes;    // offset table in front of / behind the ring, its size
     int tstart[6];
     int scatter_m;
-    int nchunk;                  // the pass covers only the tiles whose counter has chunk_or at
-    int chunk_pos[UA_MAX_CHUNK_BITS];   // these (ascending) counter bits: a 2^-nchunk slice of the state
-    unsigned long long chunk_or;
     unsigned long long tile_xor;
     int nins;
     int ins[UA_MAX_TILE_BITS + UA_MAX_SCATTER_BITS];
@@ -133,14 +130,10 @@ __global__ void __launch_bounds__(CL_TEAMS * 256 + 32, 1) cluster_ring_kernel(co
     }
 
     // tile counter -> (tensor coordinates of the source box, of the destination box, destination)
-    const int tpr_bits = a.total_bits - a.T - a.nchunk;       // log2(tiles per row visited)
+    const int tpr_bits = a.total_bits - a.T;       // log2(tiles per row)
     auto coords = [&](long long tile_id, int *cin, int *cout, int &dst) {
         const long long row = tile_id >> tpr_bits;
-        long long j = tile_id - (row << tpr_bits);
-        if (a.nchunk) {
-            for (int i = 0; i < a.nchunk; ++i) j = (long long)insert_zero((uint64_t)j, a.chunk_pos[i]);
-            j |= (long long)a.chunk_or;
-        }
+        const long long j = tile_id - (row << tpr_bits);
         uint64_t base;
         if constexpr (SCATTER) {
             base = (uint64_t)(j >> a.scatter_m) << a.L;
@@ -441,54 +434,16 @@ static void fill_cluster_geom(ClusterGeom &g, const FusedArgs &a) {
     g.nbuf = 1;
     for (int i = 0; i < 6; ++i) { g.tstart[i] = a.tstart[i]; g.tstart_out[i] = a.tstart_out[i]; }
     g.scatter_m = a.scatter_m; g.tile_xor = a.tile_xor; g.nins = a.nins;
-    g.nchunk = 0; g.chunk_or = 0;
     for (int i = 0; i < UA_MAX_TILE_BITS + UA_MAX_SCATTER_BITS; ++i) g.ins[i] = a.ins[i];
     for (int i = 0; i < UA_MAX_SCATTER_BITS; ++i) g.vpos[i] = a.vpos[i];
     g.tmap_in = a.tmap_in; g.tmap_out = a.tmap_out;
     for (int i = 0; i < (1 << UA_MAX_SCATTER_BITS); ++i) g.tmap_dst[i] = a.tmap_dst[i];
 }
 
-// Restrict a pass to the 2^-c slice of the state whose index bits `bits` (ascending, none of them
-// a tile bit or a scatter bit) have the value `index` (bit i of index <-> bits[i]).
-static int set_chunk(ClusterGeom &g, const char *who, int num_chunk_bits, const int *host_chunk_bits, int chunk_index) {
-    if (num_chunk_bits == 0) return UA_OK;
-    if (num_chunk_bits < 0 || num_chunk_bits > UA_MAX_CHUNK_BITS || !host_chunk_bits ||
-        chunk_index < 0 || chunk_index >= (1 << num_chunk_bits)) {
-        set_error("%s: bad chunk arguments (at most %d chunk bits)", who, UA_MAX_CHUNK_BITS); return UA_ERR_INVALID;
-    }
-    if (g.total_bits - g.T - g.scatter_m < num_chunk_bits) { set_error("%s: more chunk bits than free index bits", who); return UA_ERR_INVALID; }
-    for (int i = 0; i < num_chunk_bits; ++i) {
-        const int p = host_chunk_bits[i];
-        if (p < g.L || p >= g.total_bits || (i > 0 && p <= host_chunk_bits[i - 1])) {
-            set_error("%s: chunk bits must be ascending in [tile_low_bits, total_bits)", who); return UA_ERR_INVALID;
-        }
-        int below = g.L;                       // tile / scatter bits below p are not counter bits
-        for (int h = 0; h < g.H; ++h) {
-            if (g.high[h] == p) { set_error("%s: chunk bit %d is a tile bit", who, p); return UA_ERR_INVALID; }
-            if (g.high[h] < p) ++below;
-        }
-        int pos = p - below;
-        if (g.scatter_m) {                      // counter = [other free bits][scatter bits]
-            for (int v = 0; v < g.scatter_m; ++v) {
-                if (g.vpos[v] == p) { set_error("%s: chunk bit %d is a scatter bit", who, p); return UA_ERR_INVALID; }
-                if (g.vpos[v] < p) --pos;
-            }
-            pos += g.scatter_m;
-        }
-        g.chunk_pos[i] = pos;
-        if ((chunk_index >> i) & 1) g.chunk_or |= 1ull << pos;
-    }
-    g.nchunk = num_chunk_bits;
-    g.num_tiles >>= num_chunk_bits;
-    return UA_OK;
-}
-
 template <bool SCATTER>
-static int launch_cluster(const FusedArgs &a, const ClusterArgs &ca, cudaStream_t st, const char *who = "",
-                          int num_chunk_bits = 0, const int *host_chunk_bits = nullptr, int chunk_index = 0) {
+static int launch_cluster(const FusedArgs &a, const ClusterArgs &ca, cudaStream_t st) {
     static thread_local ClusterGeom g;
     fill_cluster_geom(g, a);
-    if (const int rc = set_chunk(g, who, num_chunk_bits, host_chunk_bits, chunk_index)) return rc;
     auto kern = cluster_ring_kernel<SCATTER>;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -541,13 +496,13 @@ static int launch_cluster(const FusedArgs &a, const ClusterArgs &ca, cudaStream_
 
 using namespace ua;
 
-static int fused_pass_hostmats_impl(const char *who, int dtype, void *out, const void *in, long long total_amps,
-                                    int total_bits, int tile_low_bits, int num_high,
-                                    const int *host_high_pos, int num_gates, const int *host_gate_k,
-                                    const int *host_gate_bits, const long long *host_gate_offset,
-                                    const void *host_gate_mats, int adjoint, int num_chunk_bits,
-                                    const int *host_chunk_bits, int chunk_index, void *stream) {
+extern "C" int ua_apply_fused_pass_hostmats(int dtype, void *out, const void *in, long long total_amps,
+                                            int total_bits, int tile_low_bits, int num_high,
+                                            const int *host_high_pos, int num_gates, const int *host_gate_k,
+                                            const int *host_gate_bits, const long long *host_gate_offset,
+                                            const void *host_gate_mats, int adjoint, void *stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const char *who = "ua_apply_fused_pass_hostmats";
     if (dtype != UA_C64) { set_error("%s: complex64 only", who); return UA_ERR_UNSUPPORTED; }
     FusedArgs a{};
     int mat_elems = 0;
@@ -570,39 +525,17 @@ static int fused_pass_hostmats_impl(const char *who, int dtype, void *out, const
     a.mats = nullptr;
     a.trank = 0;
     if (!setup_tensor_maps(a, 0, total_amps, true)) { set_error("%s: the tile needs more than 5 TMA dimensions", who); return UA_ERR_UNSUPPORTED; }
-    return launch_cluster<false>(a, ca, st, who, num_chunk_bits, host_chunk_bits, chunk_index);
+    return launch_cluster<false>(a, ca, st);
 }
 
-extern "C" int ua_apply_fused_pass_hostmats(int dtype, void *out, const void *in, long long total_amps,
-                                            int total_bits, int tile_low_bits, int num_high,
-                                            const int *host_high_pos, int num_gates, const int *host_gate_k,
-                                            const int *host_gate_bits, const long long *host_gate_offset,
-                                            const void *host_gate_mats, int adjoint, void *stream) {
-    return fused_pass_hostmats_impl("ua_apply_fused_pass_hostmats", dtype, out, in, total_amps, total_bits,
-                                    tile_low_bits, num_high, host_high_pos, num_gates, host_gate_k, host_gate_bits,
-                                    host_gate_offset, host_gate_mats, adjoint, 0, nullptr, 0, stream);
-}
-
-extern "C" int ua_apply_fused_pass_hostmats_chunk(int dtype, void *out, const void *in, long long total_amps,
-                                                  int total_bits, int tile_low_bits, int num_high,
-                                                  const int *host_high_pos, int num_gates, const int *host_gate_k,
-                                                  const int *host_gate_bits, const long long *host_gate_offset,
-                                                  const void *host_gate_mats, int adjoint, int num_chunk_bits,
-                                                  const int *host_chunk_bits, int chunk_index, void *stream) {
-    return fused_pass_hostmats_impl("ua_apply_fused_pass_hostmats_chunk", dtype, out, in, total_amps, total_bits,
-                                    tile_low_bits, num_high, host_high_pos, num_gates, host_gate_k, host_gate_bits,
-                                    host_gate_offset, host_gate_mats, adjoint, num_chunk_bits, host_chunk_bits,
-                                    chunk_index, stream);
-}
-
-static int fused_pass_scatter_hostmats_impl(const char *who, int dtype, const void *in, long long total_amps, int total_bits,
-                                            int tile_low_bits, int num_high, const int *host_high_pos,
-                                            int num_gates, const int *host_gate_k, const int *host_gate_bits,
-                                            const long long *host_gate_offset, const void *host_gate_mats,
-                                            int num_scatter_bits, const int *host_scatter_pos,
-                                            void *const *host_dst_ptrs, int visit_xor, int num_chunk_bits,
-                                            const int *host_chunk_bits, int chunk_index, void *stream) {
+extern "C" int ua_apply_fused_pass_scatter_hostmats(int dtype, const void *in, long long total_amps, int total_bits,
+                                                    int tile_low_bits, int num_high, const int *host_high_pos,
+                                                    int num_gates, const int *host_gate_k, const int *host_gate_bits,
+                                                    const long long *host_gate_offset, const void *host_gate_mats,
+                                                    int num_scatter_bits, const int *host_scatter_pos,
+                                                    void *const *host_dst_ptrs, int visit_xor, void *stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const char *who = "ua_apply_fused_pass_scatter_hostmats";
     if (dtype != UA_C64) { set_error("%s: complex64 only", who); return UA_ERR_UNSUPPORTED; }
     if (num_scatter_bits < 1 || num_scatter_bits > UA_MAX_SCATTER_BITS || !host_scatter_pos || !host_dst_ptrs) {
         set_error("%s: num_scatter_bits=%d out of range (1..%d) or null pointer", who, num_scatter_bits, UA_MAX_SCATTER_BITS);
@@ -626,31 +559,5 @@ static int fused_pass_scatter_hostmats_impl(const char *who, int dtype, const vo
     a.mats = nullptr;
     a.trank = 0;
     if (!setup_tensor_maps(a, 0, total_amps, true)) { set_error("%s: the tile needs more than 5 TMA dimensions", who); return UA_ERR_UNSUPPORTED; }
-    return launch_cluster<true>(a, ca, st, who, num_chunk_bits, host_chunk_bits, chunk_index);
-}
-
-extern "C" int ua_apply_fused_pass_scatter_hostmats(int dtype, const void *in, long long total_amps, int total_bits,
-                                                    int tile_low_bits, int num_high, const int *host_high_pos,
-                                                    int num_gates, const int *host_gate_k, const int *host_gate_bits,
-                                                    const long long *host_gate_offset, const void *host_gate_mats,
-                                                    int num_scatter_bits, const int *host_scatter_pos,
-                                                    void *const *host_dst_ptrs, int visit_xor, void *stream) {
-    return fused_pass_scatter_hostmats_impl("ua_apply_fused_pass_scatter_hostmats", dtype, in, total_amps, total_bits,
-                                            tile_low_bits, num_high, host_high_pos, num_gates, host_gate_k,
-                                            host_gate_bits, host_gate_offset, host_gate_mats, num_scatter_bits,
-                                            host_scatter_pos, host_dst_ptrs, visit_xor, 0, nullptr, 0, stream);
-}
-
-extern "C" int ua_apply_fused_pass_scatter_hostmats_chunk(int dtype, const void *in, long long total_amps, int total_bits,
-                                                          int tile_low_bits, int num_high, const int *host_high_pos,
-                                                          int num_gates, const int *host_gate_k, const int *host_gate_bits,
-                                                          const long long *host_gate_offset, const void *host_gate_mats,
-                                                          int num_scatter_bits, const int *host_scatter_pos,
-                                                          void *const *host_dst_ptrs, int visit_xor, int num_chunk_bits,
-                                                          const int *host_chunk_bits, int chunk_index, void *stream) {
-    return fused_pass_scatter_hostmats_impl("ua_apply_fused_pass_scatter_hostmats_chunk", dtype, in, total_amps,
-                                            total_bits, tile_low_bits, num_high, host_high_pos, num_gates, host_gate_k,
-                                            host_gate_bits, host_gate_offset, host_gate_mats, num_scatter_bits,
-                                            host_scatter_pos, host_dst_ptrs, visit_xor, num_chunk_bits,
-                                            host_chunk_bits, chunk_index, stream);
+    return launch_cluster<true>(a, ca, st);
 }

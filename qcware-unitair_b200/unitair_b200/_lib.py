@@ -21,7 +21,6 @@ UA_ERR_UNSUPPORTED = 2
 MAX_GATE_QUBITS = 5
 MAX_GENERIC_GATE_QUBITS = 10
 MAX_FUSED_GATES = 64
-MAX_CHUNK_BITS = 3          # UA_MAX_CHUNK_BITS
 
 _lib = None
 
@@ -82,13 +81,6 @@ def _declare(L):
     L.ua_apply_fused_pass_scatter_hostmats.argtypes = [c_int, c_void_p, c_longlong, c_int, c_int, c_int, p_int,
                                                        c_int, p_int, p_int, p_ll, c_void_p, c_int, p_int,
                                                        POINTER(c_void_p), c_int, c_void_p]
-    L.ua_apply_fused_pass_hostmats_chunk.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
-                                                     p_int, c_int, p_int, p_int, p_ll, c_void_p, c_int,
-                                                     c_int, p_int, c_int, c_void_p]
-    L.ua_apply_fused_pass_scatter_hostmats_chunk.argtypes = [c_int, c_void_p, c_longlong, c_int, c_int, c_int, p_int,
-                                                             c_int, p_int, p_int, p_ll, c_void_p, c_int, p_int,
-                                                             POINTER(c_void_p), c_int, c_int, p_int, c_int, c_void_p]
-    L.ua_peer_copy.argtypes = [c_void_p, c_void_p, c_longlong, c_void_p]
     L.ua_fused_backward_pass.argtypes = [c_int, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int,
                                          p_int, c_int, p_int, p_int, p_ll, c_void_p, c_longlong,
                                          p_int, c_void_p, c_void_p]
@@ -108,8 +100,7 @@ def _declare(L):
                  "ua_abs_squared", "ua_norm_squared", "ua_diag_expectation", "ua_inner_product",
                  "ua_fused_limits", "ua_real_scale", "ua_apply_fused_pass", "ua_fused_backward_pass", "ua_permute_bits",
                  "ua_apply_fused_pass_scatter", "ua_apply_fused_pass_hostmats",
-                 "ua_apply_fused_pass_scatter_hostmats", "ua_apply_fused_pass_hostmats_chunk",
-                 "ua_apply_fused_pass_scatter_hostmats_chunk", "ua_peer_copy", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close",
+                 "ua_apply_fused_pass_scatter_hostmats", "ua_ipc_export", "ua_ipc_open", "ua_ipc_close",
                  "ua_sample_block_sums", "ua_sample_locate"):
         getattr(L, name).restype = c_int
 

@@ -147,13 +147,9 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
     gate_bits[g] are the index-bit positions gate g acts on.  Gates are only reordered
     across gates they share no bit with (a skipped gate blocks its bits for the rest of
     the pass), so the product of the passes equals the original circuit.
-    forbidden_first: bit positions that must not be tile bits of the FIRST pass; a list of
-    sets bans positions in the first len(list) passes (entry i for pass i).
+    forbidden_first: bit positions that must not be tile bits of the FIRST pass.
     """
-    if forbidden_first and isinstance(forbidden_first[0], (set, frozenset, list, tuple)):
-        forbidden_seq = [set(f) for f in forbidden_first]
-    else:
-        forbidden_seq = [set(forbidden_first or ())]
+    forbidden = set(forbidden_first or ())
     n_gates = len(gate_bits)
     done = [False] * n_gates
     passes: List[Pass] = []
@@ -163,7 +159,7 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
             first += 1
             continue
         k0 = len(gate_bits[first])
-        banned = forbidden_seq[len(passes)] if len(passes) < len(forbidden_seq) else set()
+        banned = forbidden if not passes else set()
         if k0 > max_fused_k:
             passes.append(Pass(high=[], gates=[first], direct=True))
             done[first] = True
@@ -198,8 +194,8 @@ def plan_passes(gate_bits: Sequence[Sequence[int]], geo: TileGeometry,
         if not cur.gates:
             if banned:
                 # nothing fits under the ban (the first gate touches a forbidden bit): lift the
-                # ban, the caller copes (extra copy pass / shorter exchange pipeline)
-                forbidden_seq = [set() for _ in range(len(passes))]
+                # ban, the caller copes (extra copy pass)
+                forbidden = set()
                 passes.append(None)
                 continue
             # no ban and the first pending gate still does not fit a tile (tiny max_high, too
@@ -332,13 +328,12 @@ def merge_gates(gates, max_k: int = None):
 class _PassLaunch:
     """Pre-marshalled arguments of one native call (everything except the state pointers)."""
 
-    __slots__ = ("direct", "gate", "low", "nhigh", "high", "high_list", "ngates", "ks", "bits", "offs", "host_ok")
+    __slots__ = ("direct", "gate", "low", "nhigh", "high", "ngates", "ks", "bits", "offs", "host_ok")
 
     def __init__(self, p: Pass, geo: TileGeometry, gate_bits, offsets):
         self.direct = p.direct
         self.gate = p.gates[0] if p.direct else -1
         self.host_ok = False
-        self.high_list = list(p.high)
         if p.direct:
             return
         self.low = geo.tile_bits - len(p.high)
@@ -387,7 +382,7 @@ class CompiledCircuit:
     """
 
     def __init__(self, gates, num_qubits: int, dtype: torch.dtype, batch_shape=(),
-                 geometry: TileGeometry = None, merge: bool = True, tail_forbidden=None, tail_chunk=None):
+                 geometry: TileGeometry = None, merge: bool = True, tail_forbidden=None):
         from . import states
         n = num_qubits
         self.n = n
@@ -426,14 +421,7 @@ class CompiledCircuit:
         elif tail_forbidden:
             # index bits that leave the shard right after this circuit (sharded.py): plan from
             # the end so that the last pass is full and avoids them
-            # tail_chunk = (chunk bits, depth): the last `depth` passes also avoid the chunk bits,
-            # so that they can run slice by slice in front of a pipelined exchange (ScatterTail)
-            if tail_chunk and tail_chunk[0] and tail_chunk[1] > 0:
-                cb, depth = set(tail_chunk[0]), int(tail_chunk[1])
-                bans = [set(tail_forbidden) | cb] + [set(cb) for _ in range(depth - 1)]
-                self.passes = plan_passes_tail_first(self.gate_bits, self.geo, bans)
-            else:
-                self.passes = plan_passes_tail_first(self.gate_bits, self.geo, list(tail_forbidden))
+            self.passes = plan_passes_tail_first(self.gate_bits, self.geo, list(tail_forbidden))
         else:
             self.passes = plan_passes(self.gate_bits, self.geo)
         if self.gates:
@@ -569,7 +557,7 @@ class ScatterTail:
     cannot be used (it touches a victim bit, is a direct big-gate launch, or there is no
     circuit) the tail is a pure copy pass."""
 
-    def __init__(self, compiled, n: int, dtype, victim_bits, chunk_bits=None, depth: int = 0):
+    def __init__(self, compiled, n: int, dtype, victim_bits):
         vs = sorted(int(v) for v in victim_bits)
         m = len(vs)
         base = default_geometry(n, dtype)
@@ -603,36 +591,19 @@ class ScatterTail:
                 raise ValueError("no room for a scatter tile")
             launch = _PassLaunch(Pass(high=high, gates=[]), geo, [], [])
         self.launch = launch
-        # pipelined exchange: the last `pipe_depth` passes (the scatter pass included) avoid the
-        # chunk bits and can run slice by slice (run_staged)
-        self.chunk_bits = None
-        self.pipe_depth = 0
-        cb = sorted(int(b) for b in (chunk_bits or ()))
-        if cb and depth > 0 and self.reused and launch.host_ok and compiled.mats_host is not None \
-                and len(cb) <= L.MAX_CHUNK_BITS and not (set(cb) & (set(launch.high_list) | set(vs))) \
-                and min(cb) >= launch.low and n - compiled.geo.tile_bits - m >= len(cb):
-            d = 1
-            for pl in reversed(self.inplace_launches):
-                if d >= depth or pl.direct or not pl.host_ok or (set(cb) & set(pl.high_list)) or min(cb) < pl.low:
-                    break
-                d += 1
-            self.chunk_bits = cb
-            self._chunk_arr = L.int_array(cb)
-            self.pipe_depth = d
 
     @property
     def num_passes(self):
         return len(self.inplace_launches) + 1
 
-    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None, visit_xor: int = 0, mark=None,
-            skip_inplace: bool = False):
+    def run(self, state: torch.Tensor, dst_ptrs, before_scatter=None, visit_xor: int = 0, mark=None):
         """In-place passes on `state`, then the tail pass from `state` into the 2^m destination
         blocks `dst_ptrs` (device addresses, possibly of peer GPUs).  `before_scatter` is called
         right before the scatter pass is enqueued (cross-rank fence when the destinations may
         still be in use).  visit_xor: see ua_apply_fused_pass_scatter (rank-dependent tile order).
         mark: optional callback(tag) for phase timing, called after the in-place passes."""
         cc = self.compiled
-        if self.inplace_launches and not skip_inplace:
+        if self.inplace_launches:
             cc._run_launches(self.inplace_launches, state, state)
         if before_scatter is not None:
             before_scatter()
@@ -655,104 +626,6 @@ class ScatterTail:
                 L.dtype_code(self.dtype), state.data_ptr(), 1 << self.n, self.n, pl.low, pl.nhigh, pl.high,
                 pl.ngates, pl.ks, pl.bits, pl.offs, cc._device_mats(dev).data_ptr() if pl.ngates else None,
                 self.m, self.victims, L.ptr_array(list(dst_ptrs)), int(visit_xor), L.stream_ptr(dev)))
-
-
-    def run_staged(self, state: torch.Tensor, stage: torch.Tensor, dst_ptrs, order, copy_streams,
-                   before_scatter=None, mark=None) -> bool:
-        """Pipelined form of run(): the last pipe_depth passes are executed slice by slice (2^c
-        slices selected by the chunk bits, which are the top index bits that stay in the shard);
-        the scatter pass of a slice writes into `stage` (a private buffer of the shard's size, in
-        the squeezed layout of the exchange) and the finished slice of every destination block is
-        sent to dst_ptrs[b] by the copy engines on `copy_streams` while the SMs work on the next
-        slices.  order: the sequence in which the blocks are sent.  Returns False when a pass
-        turns out not to fit the register-blocked kernel: the in-place passes have then been
-        executed in full and the caller finishes with run(..., skip_inplace=True)."""
-        cc = self.compiled
-        dev = state.device
-        lib = L.lib()
-        code = L.dtype_code(self.dtype)
-        n, m = self.n, self.m
-        c = len(self.chunk_bits)
-        d = self.pipe_depth
-        cut = len(self.inplace_launches) - (d - 1)
-        pipe = self.inplace_launches[cut:]
-        esz = state.element_size()
-        block_bytes = (esz << n) >> m
-        sub = block_bytes >> c
-        stage_ptr = stage.data_ptr()
-        stage_dst = L.ptr_array([stage_ptr + b * block_bytes for b in range(1 << m)])
-        sp = state.data_ptr()
-        cur = torch.cuda.current_stream(dev)
-
-        def inplace_chunk(pl, k, stream):
-            return lib.ua_apply_fused_pass_hostmats_chunk(
-                code, sp, sp, 1 << n, n, pl.low, pl.nhigh, pl.high, pl.ngates, pl.ks, pl.bits, pl.offs,
-                cc._mats_host_ptr, 0, c, self._chunk_arr, k, stream)
-
-        def scatter_chunk(k, stream):
-            pl = self.launch
-            return lib.ua_apply_fused_pass_scatter_hostmats_chunk(
-                code, sp, 1 << n, n, pl.low, pl.nhigh, pl.high, pl.ngates, pl.ks, pl.bits, pl.offs,
-                cc._mats_host_ptr, m, self.victims, stage_dst, 0, c, self._chunk_arr, k, stream)
-
-        with L.on_device(dev):
-            stream = L.stream_ptr(dev)
-            if cut:
-                cc._run_launches(self.inplace_launches[:cut], state, state)
-            # slice 0 doubles as the check that every pipelined pass fits the kernel
-            done = 0
-            failed = False
-            for pl in pipe:
-                rc = inplace_chunk(pl, 0, stream)
-                if rc == L.UA_ERR_UNSUPPORTED:
-                    failed = True
-                    break
-                L.check(rc)
-                done += 1
-            if not failed:
-                if before_scatter is not None:
-                    before_scatter()
-                rc = scatter_chunk(0, stream)
-                if rc == L.UA_ERR_UNSUPPORTED:
-                    failed = True
-                else:
-                    L.check(rc)
-            if failed:
-                # finish the passes that did run on slice 0 for the other slices, leave the rest
-                # to the one-kernel scatter pass
-                for pl in pipe[:done]:
-                    for k in range(1, 1 << c):
-                        L.check(inplace_chunk(pl, k, stream))
-                self.chunk_bits = None
-                self.pipe_depth = 0
-                if done < len(pipe):
-                    cc._run_launches(pipe[done:], state, state)
-                return False
-            spans = getattr(self, "copy_spans", None)       # device-time bookkeeping (sharded.py, timing=)
-            for k in range(1 << c):
-                if k:
-                    for pl in pipe:
-                        L.check(inplace_chunk(pl, k, stream))
-                    L.check(scatter_chunk(k, stream))
-                ev = torch.cuda.Event(enable_timing=spans is not None and k == 0)
-                ev.record(cur)
-                if spans is not None and k == 0:
-                    first = ev
-                # the blocks of a slice are spread over the copy streams (two copy engines at work)
-                for cs in copy_streams:
-                    cs.wait_event(ev)
-                for i, b in enumerate(order):
-                    csp = copy_streams[i % len(copy_streams)].cuda_stream
-                    L.check(lib.ua_peer_copy(dst_ptrs[b] + k * sub, stage_ptr + b * block_bytes + k * sub, sub, csp))
-            if mark is not None:
-                mark("gates")
-            for cs in copy_streams:
-                cur.wait_stream(cs)
-            if spans is not None:
-                last = torch.cuda.Event(enable_timing=True)
-                last.record(cur)
-                spans.append((first, last, sub * ((1 << m) - 1) << c))
-        return True
 
 
 class _AdjointCircuit(torch.autograd.Function):

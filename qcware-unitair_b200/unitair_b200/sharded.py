@@ -215,29 +215,7 @@ class CudaEngine:
         from . import circuit
         if not gates_local:
             return None
-        return circuit.CompiledCircuit(gates_local, n_local, self.dtype, tail_forbidden=tail_victims,
-                                       tail_chunk=self.pipeline_chunk(n_local, tail_victims))
-
-    # pipelined exchange (complex64): the last passes of an epoch run slice by slice and the copy
-    # engines send a finished slice to the peers while the SMs work on the next one.
-    # UA_EXCHANGE_PIPELINE = number of passes in the pipeline (0: off, the scatter pass stores
-    # straight into the peers' memory), UA_EXCHANGE_CHUNK_BITS = log2(slices).
-    def pipeline_chunk(self, n_local, victim_bits):
-        from . import circuit
-        depth = int(os.environ.get("UA_EXCHANGE_PIPELINE", "3"))
-        c = int(os.environ.get("UA_EXCHANGE_CHUNK_BITS", "3"))
-        if not victim_bits or depth <= 0 or c <= 0 or self.dtype != torch.complex64 or not circuit.use_cluster_path():
-            return None
-        geo = circuit.default_geometry(n_local, self.dtype, cluster=True)
-        c = min(c, n_local - geo.tile_bits - len(victim_bits))
-        if c <= 0:
-            return None
-        # the top c index bits that stay in the shard: slice k of every destination block of the
-        # exchange is then one contiguous range
-        stay = [b for b in range(n_local - 1, -1, -1) if b not in set(victim_bits)][:c]
-        if min(stay) < geo.low_bits:
-            return None
-        return sorted(stay), depth
+        return circuit.CompiledCircuit(gates_local, n_local, self.dtype, tail_forbidden=tail_victims)
 
     def run(self, compiled, shard):
         if compiled is not None:
@@ -258,10 +236,7 @@ class CudaEngine:
 
     def scatter_tail(self, compiled, n_local, victim_bits):
         from . import circuit
-        chunk = self.pipeline_chunk(n_local, victim_bits)
-        if chunk is None:
-            return circuit.ScatterTail(compiled, n_local, self.dtype, victim_bits)
-        return circuit.ScatterTail(compiled, n_local, self.dtype, victim_bits, chunk_bits=chunk[0], depth=chunk[1])
+        return circuit.ScatterTail(compiled, n_local, self.dtype, victim_bits)
 
     def run_scatter(self, tail, st, ep, before_scatter=None, mark=None):
         """The epoch's passes with the last one storing into the peers' spare buffers: block b of
@@ -273,22 +248,9 @@ class CudaEngine:
         a = exchange_block_id(st.rank, ep)
         spare_of = peers[st._spare().data_ptr()]
         dst = [spare_of[exchange_peer(st.rank, ep, b)] + a * block_bytes for b in range(1 << m)]
-        skip = False
-        if getattr(tail, "chunk_bits", None):
-            stage = st.stage_buffer()
-            if stage is not None:
-                # pipelined: slices are staged locally and sent by the copy engines; every rank
-                # starts with a different peer
-                order = [b ^ a for b in range(1 << m)]
-                order = order[1:] + order[:1]          # the rank's own block last
-                if tail.run_staged(st.local, stage, dst, order, st.copy_streams(),
-                                   before_scatter=before_scatter, mark=mark):
-                    st.staged_exchanges = getattr(st, "staged_exchanges", 0) + 1
-                    return
-                skip = True
         # visit order rotated by this rank's own block number: at any moment every rank of the
         # exchange group is writing to a different peer
-        tail.run(st.local, dst, before_scatter=before_scatter, visit_xor=a, mark=mark, skip_inplace=skip)
+        tail.run(st.local, dst, before_scatter=before_scatter, visit_xor=a, mark=mark)
 
     def permute(self, src_bits, shard, out):
         from . import _lib as L
@@ -337,29 +299,6 @@ class ShardedState:
         if self.spare is None:
             self.spare = torch.empty_like(self.local)
         return self.spare
-
-    def stage_buffer(self):
-        """Third buffer of the shard's size for the pipelined exchange (private, not mapped by the
-        peers); None when device memory does not allow it (the exchange then stores directly)."""
-        if getattr(self, "_stage", None) is None:
-            if getattr(self, "_stage_refused", False):
-                return None
-            need = self.local.numel() * self.local.element_size()
-            free = torch.cuda.mem_get_info(self.local.device)[0]
-            # what this rank can see is not what every rank can see: agree on the answer
-            ok = torch.tensor([1 if free > need + (2 << 30) else 0], dtype=torch.int32, device=self.local.device)
-            if self.world > 1:
-                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
-            if int(ok.item()) == 0:
-                self._stage_refused = True
-                return None
-            self._stage = torch.empty_like(self.local)
-        return self._stage
-
-    def copy_streams(self):
-        if getattr(self, "_copy_streams", None) is None:
-            self._copy_streams = [torch.cuda.Stream(self.local.device) for _ in range(2)]
-        return self._copy_streams
 
     # -- peer memory: every rank maps the two buffers of every other rank (CUDA IPC) ---------
     def peer_pointers(self):
@@ -571,9 +510,6 @@ class ShardedCircuit:
                 ev.record()
                 marks.append((tag, ev))
 
-        for t in self.tails:
-            if t is not None and hasattr(t, "chunk_bits"):
-                t.copy_spans = [] if (timing is not None and st.local.is_cuda) else None
         mark("start")
         # A scatter pass writes into the peers' spare buffers.  That is safe without further
         # synchronisation only if every peer is known to be past its last use of that buffer:
@@ -618,9 +554,4 @@ class ShardedCircuit:
             torch.cuda.synchronize()
             for (_, e0), (tag, e1) in zip(marks[:-1], marks[1:]):
                 timing[tag] = timing.get(tag, 0.0) + e0.elapsed_time(e1)
-            for t in self.tails:
-                for first, last, nbytes in (getattr(t, "copy_spans", None) or []):
-                    # first slice ready -> last slice delivered (waits for later slices included)
-                    timing["copy_span"] = timing.get("copy_span", 0.0) + first.elapsed_time(last)
-                    timing["copy_bytes"] = timing.get("copy_bytes", 0) + nbytes
         return st

@@ -285,87 +285,3 @@ def test_native_backward_of_real_reductions(ua):
                 assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) < tol
                 if shape[-1] % 2 == 0:
                     assert launched >= 2, "forward and backward must both be native kernels"
-
-
-# --------------------------------------------------------------------------- pipelined exchange
-@pytest.mark.parametrize("n,victims,c,depth", [(20, [19], 2, 3), (22, [13, 20], 3, 3), (22, [17, 19, 21], 3, 2),
-                                               (18, [15], 1, 4)])
-def test_staged_scatter_tail_equals_direct_tail(n, victims, c, depth):
-    """The pipelined exchange (last passes run slice by slice, finished slices sent by the copy
-    engines) against the one-kernel scatter pass, all destinations in local memory: the same
-    kernels compute the same tiles, so the result is bit-identical."""
-    from unitair_b200 import circuit
-    rng = np.random.default_rng(n + c)
-    m = len(victims)
-    stay = sorted([b for b in range(n - 1, -1, -1) if b not in victims][:c])
-    gates = []
-    for _ in range(4):
-        for q in range(n):
-            gates.append(([q], torch.as_tensor(haar(rng, 2))))
-        perm = rng.permutation(n).tolist()
-        for j in range(0, n - 1, 2):
-            gates.append(([perm[j], perm[j + 1]], torch.as_tensor(haar(rng, 4))))
-    st = torch.from_numpy(rnd_state(rng, n)).cuda()
-    block_bytes = (1 << (n - m)) * 8
-    cc0 = circuit.CompiledCircuit(gates, n, torch.complex64, tail_forbidden=victims)
-    t0 = circuit.ScatterTail(cc0, n, torch.complex64, victims)
-    want = torch.full_like(st, float("nan"))
-    w0 = st.clone()
-    t0.run(w0, [want.data_ptr() + b * block_bytes for b in range(1 << m)])
-    cc1 = circuit.CompiledCircuit(gates, n, torch.complex64, tail_forbidden=victims, tail_chunk=(stay, depth))
-    t1 = circuit.ScatterTail(cc1, n, torch.complex64, victims, chunk_bits=stay, depth=depth)
-    assert t1.chunk_bits == stay and 1 <= t1.pipe_depth <= depth
-    got = torch.full_like(st, float("nan"))
-    stage = torch.full_like(st, float("nan"))
-    w1 = st.clone()
-    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
-    order = list(range(1, 1 << m)) + [0]
-    assert t1.run_staged(w1, stage, [got.data_ptr() + b * block_bytes for b in range(1 << m)], order, streams)
-    torch.cuda.synchronize()
-    # the two plans may cut the passes differently (chunk bits are banned from the last passes):
-    # compare with the tolerance of a re-planned circuit, and bit-exactly against the same plan
-    # run through the one-kernel tail
-    assert_close(got.cpu().numpy(), want.cpu().numpy(), "c64", what="staged vs direct tail")
-    same = torch.full_like(st, float("nan"))
-    w2 = st.clone()
-    t2 = circuit.ScatterTail(cc1, n, torch.complex64, victims)
-    t2.run(w2, [same.data_ptr() + b * block_bytes for b in range(1 << m)])
-    torch.cuda.synchronize()
-    assert torch.equal(torch.view_as_real(got), torch.view_as_real(same))
-
-
-def test_chunked_pass_covers_exactly_its_slice():
-    from unitair_b200 import _lib as L
-    n = 16
-    rng = np.random.default_rng(3)
-    st = torch.from_numpy(rnd_state(rng, n)).cuda()
-    u = np.ascontiguousarray(haar(rng, 4))
-    lib = L.lib()
-    stream = L.stream_ptr(st.device)
-    high = [7, 8, 10, 12, 13]
-    args = (0, None, None, 1 << n, n, 7, len(high), L.int_array(high), 1, L.int_array([2]), L.int_array([3, 10, 0]),
-            L.ll_array([0]), u.ctypes.data, 0)
-
-    def call(out, inp, cb, k):
-        a = list(args)
-        a[1], a[2] = out.data_ptr(), inp.data_ptr()
-        return lib.ua_apply_fused_pass_hostmats_chunk(*a, len(cb), L.int_array(cb) if cb else None, k, stream)
-    full = torch.empty_like(st)
-    assert call(full, st, [], 0) == 0
-    out = torch.full_like(st, float("nan"))
-    for k in range(4):
-        assert call(out, st, [9, 15], k) == 0
-    torch.cuda.synchronize()
-    assert torch.equal(torch.view_as_real(out), torch.view_as_real(full))
-    one = torch.full_like(st, float("nan"))
-    assert call(one, st, [9, 15], 2) == 0          # bit 9 = 0, bit 15 = 1
-    torch.cuda.synchronize()
-    idx = torch.arange(1 << n, device="cuda")
-    sel = ((idx >> 9) & 1 == 0) & ((idx >> 15) & 1 == 1)
-    assert torch.equal(torch.view_as_real(one[sel]), torch.view_as_real(full[sel]))
-    assert torch.isnan(one[~sel].real).all()      # untouched outside the slice
-    assert call(out, st, [10, 15], 0) != 0         # a tile bit
-    assert call(out, st, [15, 9], 0) != 0          # not ascending
-    assert call(out, st, [9, 15], 4) != 0          # slice index out of range
-    assert call(out, st, [3], 0) != 0              # among the low bits
-    assert call(out, st, [9, 11, 14, 15], 0) != 0  # too many
