@@ -15,7 +15,14 @@
 
 namespace ua {
 
-constexpr int CL_TEAMS = 3;          // 256-thread teams per CTA (+ one producer warp)
+#ifndef UA_CL_TEAMS
+#define UA_CL_TEAMS 3
+#endif
+#ifndef UA_CL_TT
+#define UA_CL_TT 256
+#endif
+constexpr int CL_TEAMS = UA_CL_TEAMS;   // teams per CTA (+ one producer warp)
+constexpr int CL_TT = UA_CL_TT;         // threads per team
 constexpr int CL_BITS = 4;
 constexpr int CL_TAB = 8;            // (cluster, sweep) slots of the per-thread group-offset table
 constexpr int CL_MAX_GATES = UA_MAX_FUSED_GATES;
@@ -82,7 +89,7 @@ __device__ __forceinline__ void sts128(unsigned addr, float4 v) {
 }
 
 __device__ __forceinline__ void team_barrier(int team) {
-    asm volatile("bar.sync %0, 256;" ::"r"(1 + team) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "n"(CL_TT) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
@@ -98,9 +105,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 // (LDS / STS / barrier) overlap another's FMA phase.  nbuf is a multiple of TEAMS (launcher), so a
 // buffer and its two mbarriers are only ever used by one team and the producer.
 template <bool SCATTER>
-__global__ void __launch_bounds__(CL_TEAMS * 256 + 32, 1) cluster_ring_kernel(const __grid_constant__ ClusterGeom a,
+__global__ void __launch_bounds__(CL_TEAMS * CL_TT + 32, 1) cluster_ring_kernel(const __grid_constant__ ClusterGeom a,
                                                                           const __grid_constant__ ClusterArgs ca) {
-    constexpr int TEAMS = CL_TEAMS, TT = 256, MAXB = 8;
+    constexpr int TEAMS = CL_TEAMS, TT = CL_TT, MAXB = 8;
     constexpr int ARITH = 1;         // packed FFMA2 (the scalar FFMA form measured 13-35 % slower, profiles/)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar_full[MAXB], bar_done[MAXB];
@@ -481,14 +488,14 @@ static int launch_cluster(const FusedArgs &a, const ClusterArgs &ca, cudaStream_
     // (TMA loads complete out of order) and the parity test would pass one phase early (seen as a
     // hang with 5 buffers, profiles/r02_ring_hang_nbuf5.txt).
     nbuf -= nbuf % CL_TEAMS;
-    if (nbuf < 2 * CL_TEAMS) { set_error("register-blocked pass: %d tile buffers of %zu bytes do not fit", 2 * CL_TEAMS, buf_bytes); return UA_ERR_UNSUPPORTED; }
+    if (nbuf < (CL_TEAMS > 3 ? CL_TEAMS : 2 * CL_TEAMS)) { set_error("register-blocked pass: %d tile buffers of %zu bytes do not fit", 2 * CL_TEAMS, buf_bytes); return UA_ERR_UNSUPPORTED; }
     g.nbuf = nbuf;
     g.tab_front = front ? 1 : 0;
     g.tab_bytes = (int)tab_bytes;
     const size_t smem = front ? (size_t)(nbuf + 1) * buf_bytes - 1024 : (size_t)(nbuf + 1) * buf_bytes + tab_bytes;
     long long grid = sms;
     if (grid > g.num_tiles) grid = g.num_tiles;
-    kern<<<(unsigned)grid, CL_TEAMS * 256 + 32, smem, st>>>(g, ca);
+    kern<<<(unsigned)grid, CL_TEAMS * CL_TT + 32, smem, st>>>(g, ca);
     return check_launch("cluster_ring_kernel");
 }
 

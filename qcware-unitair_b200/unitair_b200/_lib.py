@@ -14,7 +14,8 @@ from ctypes import c_int, c_longlong, c_size_t, c_void_p, c_char_p, c_ulonglong,
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libunitair_b200.so")
+# UA_LIB_PATH: a differently built library for A/B measurements (tools/); the default is the in-tree build
+LIB_PATH = os.environ.get("UA_LIB_PATH") or os.path.join(_HERE, "lib", "libunitair_b200.so")
 
 UA_C64, UA_C128 = 0, 1
 UA_ERR_UNSUPPORTED = 2
