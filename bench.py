@@ -309,9 +309,11 @@ def sharded_parity_check(world, rank, dev, n_total=24, layers=3, seed=77):
     return out
 
 
-def timed_sharded_run(n_total, layers, seed, world, rank, dev, exchange_mode, warm, steps):
+def timed_sharded_run(n_total, layers, seed, world, rank, dev, exchange_mode, warm, steps, joint=True):
     """The bench circuit on an n_total-qubit state over `world` ranks (world == 1: single-GPU
-    engine): device time per step (max over ranks), norm check after the timed steps."""
+    engine): device time per step (max over ranks), norm check after the timed steps.
+    joint: the warm-up steps and the timed steps are each planned as ONE gate list (as the main
+    measurement does); False: one plan per step, chained through the qubit layout."""
     import torch
     import torch.distributed as dist
     from unitair_b200 import circuit, sharded, _lib
@@ -341,18 +343,27 @@ def timed_sharded_run(n_total, layers, seed, world, rank, dev, exchange_mode, wa
     else:
         sstate = sharded.ShardedState.zero_state(n_total, torch.complex64, dev)
         plans, layout = [], sharded.identity_layout(n_total)
-        for _ in range(warm + steps):
-            pl_ = sharded.ShardedCircuit(gates, n_total, torch.complex64, world, layout=layout, restore=False,
-                                         exchange=exchange_mode)
-            plans.append(pl_)
-            layout = pl_.end_layout
-        for pl_ in plans[:warm]:
+        if joint:
+            for reps in (warm, steps):
+                pl_ = sharded.ShardedCircuit(gates * reps, n_total, torch.complex64, world, layout=layout,
+                                             restore=False, exchange=exchange_mode)
+                plans.append(pl_)
+                layout = pl_.end_layout
+            n_warm_plans = 1
+        else:
+            for _ in range(warm + steps):
+                pl_ = sharded.ShardedCircuit(gates, n_total, torch.complex64, world, layout=layout, restore=False,
+                                             exchange=exchange_mode)
+                plans.append(pl_)
+                layout = pl_.end_layout
+            n_warm_plans = warm
+        for pl_ in plans[:n_warm_plans]:
             pl_.run(sstate)
         dist.barrier()
         torch.cuda.synchronize()
         l0 = _lib.launch_count()
         e0.record()
-        for pl_ in plans[warm:]:
+        for pl_ in plans[n_warm_plans:]:
             pl_.run(sstate)
         e1.record()
         dist.barrier()
@@ -362,10 +373,11 @@ def timed_sharded_run(n_total, layers, seed, world, rank, dev, exchange_mode, wa
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed = float(t.item())
         nrm = float(sstate.norm_squared().item())
-        timed = plans[warm:]
-        info = {"passes_per_step": sum(p_.num_passes for p_ in timed) / len(timed),
-                "swaps_per_step": sum(p_.num_swaps for p_ in timed) / len(timed),
-                "swap_bytes_per_gpu_per_step": sum(p_.swap_bytes_per_step for p_ in timed) / len(timed)}
+        timed = plans[n_warm_plans:]
+        info = {"passes_per_step": sum(p_.num_passes for p_ in timed) / steps,
+                "swaps_per_step": sum(p_.num_swaps for p_ in timed) / steps,
+                "swap_bytes_per_gpu_per_step": sum(p_.swap_bytes_per_step for p_ in timed) / steps,
+                "planning": "timed steps planned as one gate list" if joint else "one plan per step"}
         sstate.release_peers()
         del sstate, plans
     torch.cuda.empty_cache()
@@ -423,22 +435,23 @@ def run_ours(args):
         from unitair_b200 import sharded
         sstate = sharded.ShardedState.zero_state(n_total, torch.complex64, dev)
         # Every step applies the same 10-layer circuit to the state the previous step left, i.e.
-        # the steps together are one deep circuit.  The qubit layout is carried from step to step
-        # (no swap-back at the end of a step), so each step has its own pre-built plan, exactly
-        # as the single-GPU arm pre-compiles its circuit outside the timed region.
-        n_plans = max(args.warmup, 3) + args.steps
+        # the steps together are one deep circuit, and that is how they are planned: the W warm-up
+        # steps as one gate list, the K timed steps as another (pre-built outside the timed region,
+        # exactly as the single-GPU arm pre-compiles its circuit).  The qubit layout is carried
+        # over (no swap-back), and the few gates at the end of a step that wait for a global qubit
+        # share an exchange with the next step instead of paying one of their own.  The same K
+        # steps with one plan PER STEP are timed as well and reported under `per_step_plans`.
+        n_warm = max(args.warmup, 3)
 
         def build_plans(exchange):
-            out_, layout = [], sharded.identity_layout(n_total)
-            for _ in range(n_plans):
-                pl_ = sharded.ShardedCircuit(gates_dev, n_total, torch.complex64, world, layout=layout,
-                                             restore=False, exchange=exchange)
-                out_.append(pl_)
-                layout = pl_.end_layout
-            return out_
+            warm_ = sharded.ShardedCircuit(gates_dev * n_warm, n_total, torch.complex64, world,
+                                           restore=False, exchange=exchange)
+            timed_ = sharded.ShardedCircuit(gates_dev * args.steps, n_total, torch.complex64, world,
+                                            layout=warm_.end_layout, restore=False, exchange=exchange)
+            return warm_, timed_
         exchange_mode = None
-        plans = build_plans(exchange_mode)
-        if plans[0].p2p:
+        warm_plan, plan = build_plans(exchange_mode)
+        if plan.p2p:
             # peer mapping (CUDA IPC) is set up collectively on first use: if this box refuses it,
             # every rank fails the same way and falls back to the send/recv exchange -- loudly
             try:
@@ -448,33 +461,36 @@ def run_ours(args):
                     print(f"bench: peer-memory mapping failed ({e!r}); using the NCCL send/recv exchange",
                           file=sys.stderr, flush=True)
                 exchange_mode = "nccl"
-                plans = build_plans(exchange_mode)
-        plan_iter = iter(plans)
-        step = lambda: next(plan_iter).run(sstate)   # noqa: E731
-        timed = plans[max(args.warmup, 3):max(args.warmup, 3) + args.steps]
-        plan = plans[-1]
-        launches_per_step = sum(p_.num_passes for p_ in timed) / len(timed)
+                warm_plan, plan = build_plans(exchange_mode)
+        launches_per_step = plan.num_passes / args.steps
         kernel_name = "cluster_ring_kernel"
         extra = {"passes_per_step": launches_per_step, "gates_per_step": num_gates,
-                 "swaps_per_step": sum(p_.num_swaps for p_ in timed) / len(timed),
-                 "fused_swaps_per_step": sum(p_.num_fused_swaps for p_ in timed) / len(timed),
+                 "swaps_per_step": plan.num_swaps / args.steps,
+                 "fused_swaps_per_step": plan.num_fused_swaps / args.steps,
                  "exchange": "p2p (last pass of an epoch stores into the peers' memory)" if plan.p2p
                              else "nccl (bit permutation pass + grouped send/recv)",
-                 "swap_bytes_per_gpu_per_step": sum(p_.swap_bytes_per_step for p_ in timed) / len(timed)}
+                 "swap_bytes_per_gpu_per_step": plan.swap_bytes_per_step / args.steps,
+                 "planning": f"the {args.steps} timed steps are planned as one gate list"}
 
     check = None
     if world > 1 and not args.no_check:
         check = sharded_parity_check(world, rank, dev)
-    for _ in range(max(args.warmup, 3)):
-        step()
+    if world == 1:
+        for _ in range(max(args.warmup, 3)):
+            step()
+    else:
+        warm_plan.run(sstate)
     barrier()
     sampler.start()
     l0 = _lib.launch_count()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step()
+    if world == 1:
+        for _ in range(args.steps):
+            step()
+    else:
+        plan.run(sstate)                  # args.steps steps
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -578,6 +594,15 @@ def run_ours(args):
             del h_in, h_out
         except Exception as e:  # pragma: no cover
             line["e2e"] = {"value": None, "unit": UNIT, "error": repr(e)[:200]}
+    if world > 1 and not (args.no_extra or big):
+        # the same K steps with one plan per step (each step's leftover gates pay their own exchange)
+        try:
+            ps = timed_sharded_run(n_total, args.layers, args.seed, world, rank, dev, exchange_mode,
+                                   max(args.warmup, 3), args.steps, joint=False)
+            line["per_step_plans"] = {k: ps[k] for k in ("ms_per_step", "value", "passes_per_step", "swaps_per_step",
+                                                         "swap_bytes_per_gpu_per_step", "norm_ok", "planning")}
+        except Exception as e:  # pragma: no cover
+            line["per_step_plans"] = {"error": repr(e)[:200]}
     if world > 1:
         # untimed extra step with per-phase device timing (permute / exchange / gates), rank 0
         tm = {}
