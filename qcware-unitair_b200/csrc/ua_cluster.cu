@@ -47,7 +47,7 @@ struct ClusterArgs {
     int ncl;
     ClusterDesc cl[CL_MAX_GATES];
     ClusterGate g[CL_MAX_GATES];
-    alignas(16) float2 mats[CL_MAX_MAT_ELEMS];
+    alignas(16) float mats[3 * CL_MAX_MAT_ELEMS];   // per gate, row by row: D x gr, D x (-gi, gi)  (ua_cluster.cuh)
 };
 
 
@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(CL_TEAMS * CL_TT + 32, 1) cluster_ring_kernel(
                 }
                 for (int q = gbeg; q < gend; ++q) {
                     const ClusterGate cg = ca.g[q];
-                    // moff counts 16-byte units: the compiler can prove the alignment
-                    reg_gate_dispatch<ARITH>(v, cg.type, reinterpret_cast<const float2 *>(
+                    // moff counts 16-byte units: the compiler can prove the alignment of the row loads
+                    reg_gate_dispatch<ARITH>(v, cg.type, reinterpret_cast<const float *>(
                         reinterpret_cast<const float4 *>(ca.mats) + cg.moff));
                 }
                 if (vec16) {
@@ -406,7 +406,7 @@ static bool build_clusters(const FusedArgs &a, const float2 *host_mats, ClusterA
             const FusedGate &gd = a.gates[cls[c].gates[i]];
             const int K = gd.k, D = 1 << K;
             ClusterGate &cg = ca.g[q++];
-            cg.moff = (unsigned short)(moff / 2);
+            cg.moff = (unsigned short)(moff / 4);          // moff counts floats; 3 D^2 per gate = 48 or 12
             if (K == 1) {
                 cg.type = (unsigned char)(6 + pos_of[gd.sb[0]]);
             } else {
@@ -424,9 +424,12 @@ static bool build_clusters(const FusedArgs &a, const float2 *host_mats, ClusterA
                 float2 val;
                 if (a.adjoint) { val = src[gj * D + gi]; val.y = -val.y; }
                 else val = src[gi * D + gj];
-                ca.mats[moff + e] = val;
+                float *row = ca.mats + moff + 3 * D * sr;
+                row[t] = val.x;
+                row[D + 2 * t] = -val.y;
+                row[D + 2 * t + 1] = val.y;
             }
-            moff += D * D;
+            moff += 3 * D * D;
         }
         ca.cl[c].gend = (unsigned char)q;
     }
