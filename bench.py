@@ -422,7 +422,6 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    result = {}
     if world == 1:
         state = torch.zeros(2 ** n_total, dtype=torch.complex64, device=dev)
         state[0] = 1
@@ -712,7 +711,7 @@ def run_ours(args):
                 sstate.release_peers()
                 dist.barrier()
                 sstate.local = sstate.spare = None
-                plans = tplan = None
+                warm_plan = plan = tplan = None      # noqa: F841  (drop references before the big states)
             else:
                 state = None
             torch.cuda.empty_cache()
