@@ -726,6 +726,25 @@ def run_ours(args):
                                                                exchange_mode if world > 1 else None, warm=2, steps=3)
         except Exception as e:  # pragma: no cover
             line["extra_error"] = repr(e)[:300]
+    # BASELINE.json's other single-GPU configs at full size (C1: 10 qubits x batch 1024, C2: 24 qubits
+    # x 200 layers, C3: 16 qubits x batch 4096 forward + gradient, C4: 30 qubits complex128 with
+    # 5-qubit blocks on the FP64 tensor cores + phase layers): timings only, parity is tests/
+    if world == 1 and not args.no_extra and args.total_qubits is None and args.qubits == 30:
+        try:
+            state = None
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+            import bench_configs as bc
+            cfgs = {}
+            for name in ("c1", "c2", "c3", "c4"):
+                try:
+                    cfgs[name] = getattr(bc, name)()
+                except Exception as e:  # pragma: no cover
+                    cfgs[name] = {"error": repr(e)[:200]}
+                torch.cuda.empty_cache()
+            line["configs"] = cfgs
+        except Exception as e:  # pragma: no cover
+            line["configs"] = {"error": repr(e)[:300]}
     failed = not line["check"]["ok"]
     if rank == 0:
         print(json.dumps(line), flush=True)
