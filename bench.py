@@ -275,7 +275,9 @@ def sharded_parity_check(world, rank, dev, n_total=24, layers=3, seed=77):
     import torch.distributed as dist
     from unitair_b200 import circuit, sharded
     gates_np = random_circuit(n_total, layers, seed)
-    gates = [(qs, torch.as_tensor(u.astype(np.complex64)).to(dev)) for qs, u in gates_np]
+    # host gate tensors: the shards of this small state then go through the same register-blocked
+    # pass kernel as the timed run (device gates on a small state stay on the other pass kernel)
+    gates = [(qs, torch.as_tensor(u.astype(np.complex64))) for qs, u in gates_np]
     out = {"qubits": n_total, "layers": layers, "gates": len(gates), "tolerance": 1e-5, "ok": True}
     ref = None
     if rank == 0:

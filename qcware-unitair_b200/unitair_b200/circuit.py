@@ -252,6 +252,9 @@ def _bkron(a, b):
     return out.reshape(out.shape[:-4] + (out.shape[-4] * out.shape[-3], out.shape[-2] * out.shape[-1]))
 
 
+SMALL_STATE_AMPS = 1 << 21     # below this, device-resident gates stay on the device (no host copy)
+
+
 def use_cluster_path() -> bool:
     """The register-blocked pass kernel (matrix values as kernel parameters) is the default for
     complex64 circuits of shared 1-/2-qubit gates; UA_CLUSTER=0 keeps every pass on the
@@ -434,8 +437,11 @@ class CompiledCircuit:
         # parameters): complex64, shared gates only
         self.mats_host = None
         if self.cluster and self.row_stride == 0 and any(pl.host_ok for pl in self.launches):
-            self.mats_host = self.mats if self.gates_on_host else self.mats.cpu()
-            self._mats_host_ptr = self.mats_host.data_ptr()
+            # device gates cost one device-to-host copy (a synchronisation): not worth it for a
+            # small state, whose passes take microseconds on either kernel
+            if self.gates_on_host or (self.batch << n) >= SMALL_STATE_AMPS:
+                self.mats_host = self.mats if self.gates_on_host else self.mats.cpu()
+                self._mats_host_ptr = self.mats_host.data_ptr()
 
     def _device_mats(self, dev):
         """Packed matrices on `dev` (uploaded once when the gates were given on the host)."""

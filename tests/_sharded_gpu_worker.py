@@ -11,7 +11,9 @@ sys.path.insert(0, os.path.join(ROOT, "qcware-unitair_b200"))
 sys.path.insert(0, ROOT)
 from bench import random_circuit  # noqa: E402
 import unitair_b200 as ua  # noqa: E402
-from unitair_b200 import sharded  # noqa: E402
+from unitair_b200 import circuit, sharded  # noqa: E402
+
+circuit.SMALL_STATE_AMPS = 0      # small test states: device gates still take the register-blocked pass kernel
 
 
 def main():

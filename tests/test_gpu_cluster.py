@@ -54,6 +54,7 @@ def oracle_run(gates, st):
 def compiled(gates, n, batch_shape=(), on_host=False, cluster=True, monkeypatch=None, **kw):
     from unitair_b200 import circuit
     monkeypatch.setenv("UA_CLUSTER", "1" if cluster else "0")
+    monkeypatch.setattr(circuit, "SMALL_STATE_AMPS", 0)     # device gates take the register-blocked path at every size
     tg = [(qs, torch.from_numpy(u) if on_host else torch.from_numpy(u).cuda()) for qs, u in gates]
     return circuit.CompiledCircuit(tg, n, torch.complex64, batch_shape, **kw)
 
