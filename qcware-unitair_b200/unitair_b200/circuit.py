@@ -410,7 +410,10 @@ class CompiledCircuit:
         self.gates_on_host = bool(self.gates) and all(m.device.type == "cpu" for _, m in self.gates)
         if self.gates and not self.gates_on_host:
             L.require_cuda(*[m for _, m in self.gates])
-        if merge and os.environ.get("UA_MERGE_GATES", "1") != "0":
+        # merging costs a handful of tiny launches per gate when the gates live on the device: more
+        # than the gate phase of a small state saves (a pass holds up to 64 gates either way)
+        small_dev = bool(self.gates) and not self.gates_on_host and (self.batch << n) < SMALL_STATE_AMPS
+        if merge and not small_dev and os.environ.get("UA_MERGE_GATES", "1") != "0":
             with torch.no_grad():
                 self.gates = merge_gates(self.gates)
         # register-blocked path: complex64, shared (un-batched) gates, matrix values on the host
