@@ -361,7 +361,229 @@ struct BwdArgs {
     double2 *acc;                              // [rows or 1][mat_elems] fp64 gradient accumulators
     int mat_elems;
     unsigned long long needs_grad;             // bit g: gate g needs a gradient
+    // register-blocked form (complex64): the gates, walked in reverse, are cut into runs whose
+    // targets fit four tile bits; a thread keeps the 16 psi and 16 grad amplitudes of one group
+    // in registers for the whole run (one shared-memory round trip and one barrier per run
+    // instead of per gate).  ncl == 0: per-gate form.
+    int ncl;
+    unsigned char cl_first[UA_MAX_FUSED_GATES];    // highest gate index of the run
+    unsigned char cl_count[UA_MAX_FUSED_GATES];    // gates cl_first, cl_first - 1, ...
+    unsigned char cl_bits[UA_MAX_FUSED_GATES][4];  // ascending tile-local bits of the run
+    unsigned char gtype[UA_MAX_FUSED_GATES];       // 0..5: pair (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) of the run's bits, 6..9: single bit
 };
+
+// ---- register-blocked backward gates (complex64).  M = U^H in target-bit order (shared memory);
+//      ax/ay collect Re / Im of grad[a][b] += g[a] * conj(psi_in[b]) over the thread's group.
+template <int I, bool GRAD>
+__device__ __forceinline__ void bwd_reg_gate1(float2 (&vp)[16], float2 (&vg)[16], const float2 *__restrict__ M,
+                                              float (&ax)[16], float (&ay)[16]) {
+    const float2 m00 = M[0], m01 = M[1], m10 = M[2], m11 = M[3];
+#pragma unroll
+    for (int gi = 0; gi < 8; ++gi) {
+        const int lo = gi & ((1 << I) - 1);
+        const int b0 = ((gi >> I) << (I + 1)) | lo, b1 = b0 | (1 << I);
+        const float2 x0 = vp[b0], x1 = vp[b1], y0 = vg[b0], y1 = vg[b1];
+        float2 p0 = mk(0.f, 0.f), p1 = p0, q0 = p0, q1 = p0;
+        cfma(p0, m00, x0); cfma(p0, m01, x1);
+        cfma(p1, m10, x0); cfma(p1, m11, x1);
+        cfma(q0, m00, y0); cfma(q0, m01, y1);
+        cfma(q1, m10, y0); cfma(q1, m11, y1);
+        if constexpr (GRAD) {
+            const float2 y[2] = {y0, y1}, xin[2] = {p0, p1};
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    ax[a * 2 + b] = fmaf(y[a].x, xin[b].x, ax[a * 2 + b]);
+                    ax[a * 2 + b] = fmaf(y[a].y, xin[b].y, ax[a * 2 + b]);
+                    ay[a * 2 + b] = fmaf(y[a].y, xin[b].x, ay[a * 2 + b]);
+                    ay[a * 2 + b] = fmaf(-y[a].x, xin[b].y, ay[a * 2 + b]);
+                }
+        }
+        vp[b0] = p0; vp[b1] = p1; vg[b0] = q0; vg[b1] = q1;
+    }
+}
+
+template <int I, int J, bool GRAD>
+__device__ __forceinline__ void bwd_reg_gate2(float2 (&vp)[16], float2 (&vg)[16], const float2 *__restrict__ M,
+                                              float (&ax)[16], float (&ay)[16]) {
+    constexpr int OTHERS = 0xF & ~((1 << I) | (1 << J));
+    constexpr int O0 = (OTHERS & 1) ? 0 : (OTHERS & 2) ? 1 : (OTHERS & 4) ? 2 : 3;
+    constexpr int O1 = (OTHERS & 8) ? 3 : (OTHERS & 4) ? 2 : (OTHERS & 2) ? 1 : 0;
+#pragma unroll
+    for (int gi = 0; gi < 4; ++gi) {
+        const int base = ((gi & 1) << O0) | ((gi >> 1) << O1);
+        float2 x[4], y[4], xin[4], yin[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            x[c] = vp[base | ((c & 1) << I) | ((c >> 1) << J)];
+            y[c] = vg[base | ((c & 1) << I) | ((c >> 1) << J)];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float2 a = mk(0.f, 0.f), b = a;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float2 m = M[r * 4 + c];          // shared-memory broadcast, not held in registers
+                cfma(a, m, x[c]);
+                cfma(b, m, y[c]);
+            }
+            xin[r] = a; yin[r] = b;
+        }
+        if constexpr (GRAD) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    ax[a * 4 + b] = fmaf(y[a].x, xin[b].x, ax[a * 4 + b]);
+                    ax[a * 4 + b] = fmaf(y[a].y, xin[b].y, ax[a * 4 + b]);
+                    ay[a * 4 + b] = fmaf(y[a].y, xin[b].x, ay[a * 4 + b]);
+                    ay[a * 4 + b] = fmaf(-y[a].x, xin[b].y, ay[a * 4 + b]);
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            vp[base | ((c & 1) << I) | ((c >> 1) << J)] = xin[c];
+            vg[base | ((c & 1) << I) | ((c >> 1) << J)] = yin[c];
+        }
+    }
+}
+
+template <bool GRAD>
+__device__ __forceinline__ void bwd_reg_dispatch(float2 (&vp)[16], float2 (&vg)[16], int type, const float2 *__restrict__ M,
+                                                 float (&ax)[16], float (&ay)[16]) {
+    switch (type) {
+        case 0: bwd_reg_gate2<0, 1, GRAD>(vp, vg, M, ax, ay); break;
+        case 1: bwd_reg_gate2<0, 2, GRAD>(vp, vg, M, ax, ay); break;
+        case 2: bwd_reg_gate2<0, 3, GRAD>(vp, vg, M, ax, ay); break;
+        case 3: bwd_reg_gate2<1, 2, GRAD>(vp, vg, M, ax, ay); break;
+        case 4: bwd_reg_gate2<1, 3, GRAD>(vp, vg, M, ax, ay); break;
+        case 5: bwd_reg_gate2<2, 3, GRAD>(vp, vg, M, ax, ay); break;
+        case 6: bwd_reg_gate1<0, GRAD>(vp, vg, M, ax, ay); break;
+        case 7: bwd_reg_gate1<1, GRAD>(vp, vg, M, ax, ay); break;
+        case 8: bwd_reg_gate1<2, GRAD>(vp, vg, M, ax, ay); break;
+        default: bwd_reg_gate1<3, GRAD>(vp, vg, M, ax, ay); break;
+    }
+}
+
+// Sum N per-lane values over the warp; lane l ends up with the total of value number
+// (l >> (5 - log2 N)) (the lanes sharing those top bits all hold it).  N + log2(32 / N) - 1 shuffles.
+template <int N>
+__device__ __forceinline__ float warp_reduce_scatter(float (&v)[N], unsigned lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & (unsigned)off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = up ? v[i] : v[i + n / 2];
+            const float keep = up ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+#pragma unroll
+    for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+    return v[0];
+}
+
+// One run of gates on the two tiles, all threads of the CTA.  The tiles were written by TMA with
+// the 128-byte swizzle (element i sits at i ^ (((i >> 4) & 7) << 1)): consecutive lanes walk the
+// lowest non-run bits, and the swizzle spreads them over the banks whatever the run's bits are.
+// When bit 0 belongs to the run, members 2m and 2m+1 are one 16-byte access.
+__device__ __forceinline__ unsigned bwd_phys(unsigned i) { return i ^ (((i >> 4) & 7u) << 1); }
+
+__device__ __forceinline__ void bwd_cluster_run(float2 *tpsi, float2 *tg, const BwdArgs &ba, int c, const float2 *sM,
+                                                double2 *sAcc, int T, int nthreads) {
+    const int b0 = ba.cl_bits[c][0], b1 = ba.cl_bits[c][1], b2 = ba.cl_bits[c][2], b3 = ba.cl_bits[c][3];
+    const bool vec16 = b0 == 0;
+    const unsigned groups = 1u << (T - 4);
+    const int first = ba.cl_first[c], count = ba.cl_count[c];
+    for (unsigned g0 = 0; g0 < groups; g0 += nthreads) {
+        const unsigned grp = g0 + threadIdx.x;
+        const bool act = grp < groups;
+        unsigned base = act ? grp : 0u;
+        base = insert_zero32(base, b0);
+        base = insert_zero32(base, b1);
+        base = insert_zero32(base, b2);
+        base = insert_zero32(base, b3);
+        auto member = [&](int m) -> unsigned {
+            return bwd_phys(base | ((m & 1) << b0) | (((m >> 1) & 1) << b1) | (((m >> 2) & 1) << b2) | (((m >> 3) & 1) << b3));
+        };
+        float2 vp[16], vg[16];
+        if (vec16) {
+#pragma unroll
+            for (int m = 0; m < 16; m += 2) {
+                const unsigned idx = member(m);
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (act) {
+                    a = *reinterpret_cast<const float4 *>(tpsi + idx);
+                    b = *reinterpret_cast<const float4 *>(tg + idx);
+                }
+                vp[m] = mk(a.x, a.y); vp[m + 1] = mk(a.z, a.w);
+                vg[m] = mk(b.x, b.y); vg[m + 1] = mk(b.z, b.w);
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const unsigned idx = member(m);
+                vp[m] = act ? tpsi[idx] : mk(0.f, 0.f);
+                vg[m] = act ? tg[idx] : mk(0.f, 0.f);
+            }
+        }
+        for (int q = first; q > first - count; --q) {
+            const FusedGate &gd = ba.f.gates[q];
+            const float2 *M = sM + gd.smoff;
+            const bool grad = (ba.needs_grad >> q) & 1ull;
+            float ax[16], ay[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { ax[e] = 0.f; ay[e] = 0.f; }
+            if (grad) {
+                bwd_reg_dispatch<true>(vp, vg, ba.gtype[q], M, ax, ay);
+                // warp reduce-scatter (9 shuffles for the 8 sums of a 1-qubit gate instead of 40:
+                // every step halves the number of values a lane carries), then the lanes that hold
+                // the totals add them to the fp64 shared-memory accumulators in one go
+                const unsigned lane = threadIdx.x & 31u;
+                if (gd.k == 1) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { v[2 * e] = ax[e]; v[2 * e + 1] = ay[e]; }
+                    const float tot = warp_reduce_scatter<8>(v, lane);
+                    if ((lane & 3u) == 0) {
+                        const unsigned i = lane >> 2;
+                        double *dst = reinterpret_cast<double *>(&sAcc[gd.smoff + (i >> 1)]) + (i & 1u);
+                        atomicAdd(dst, (double)tot);
+                    }
+                } else {
+                    float v[32];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { v[2 * e] = ax[e]; v[2 * e + 1] = ay[e]; }
+                    const float tot = warp_reduce_scatter<32>(v, lane);
+                    double *dst = reinterpret_cast<double *>(&sAcc[gd.smoff + (lane >> 1)]) + (lane & 1u);
+                    atomicAdd(dst, (double)tot);
+                }
+            } else {
+                bwd_reg_dispatch<false>(vp, vg, ba.gtype[q], M, ax, ay);
+            }
+        }
+        if (act) {
+            if (vec16) {
+#pragma unroll
+                for (int m = 0; m < 16; m += 2) {
+                    const unsigned idx = member(m);
+                    *reinterpret_cast<float4 *>(tpsi + idx) = make_float4(vp[m].x, vp[m].y, vp[m + 1].x, vp[m + 1].y);
+                    *reinterpret_cast<float4 *>(tg + idx) = make_float4(vg[m].x, vg[m].y, vg[m + 1].x, vg[m + 1].y);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const unsigned idx = member(m);
+                    tpsi[idx] = vp[m];
+                    tg[idx] = vg[m];
+                }
+            }
+        }
+    }
+}
 
 template <typename R, int K, bool LOW>
 __device__ __forceinline__ void bwd_gate_smem(typename VecOf<R>::type *tpsi, typename VecOf<R>::type *tg,
@@ -494,10 +716,12 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 2 : 1) fused_bwd_kernel(
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
     const unsigned tile_bytes = (1u << a.T) * (unsigned)sizeof(C);
-    unsigned char *buf_psi = smem_raw, *buf_g = smem_raw + tile_bytes;
-    C *sM = reinterpret_cast<C *>(smem_raw + 2 * (size_t)tile_bytes);
-    double2 *sAcc = reinterpret_cast<double2 *>(smem_raw + 2 * (size_t)tile_bytes +
-                                                (((size_t)ba.mat_elems * sizeof(C) + 127) & ~(size_t)127));
+    // the swizzled tiles of the register-blocked form need 1 KiB alignment (the launcher adds the slack)
+    unsigned char *smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *buf_psi = smem_al, *buf_g = smem_al + (tile_bytes < 1024u ? 1024u : tile_bytes);
+    unsigned char *after = buf_g + (tile_bytes < 1024u ? 1024u : tile_bytes);
+    C *sM = reinterpret_cast<C *>(after);
+    double2 *sAcc = reinterpret_cast<double2 *>(after + (((size_t)ba.mat_elems * sizeof(C) + 127) & ~(size_t)127));
     const int TV = a.T - APVLOG;
     const unsigned run_bytes = (1u << a.L) * (unsigned)sizeof(C);
     const unsigned runs = 1u << a.H;
@@ -598,7 +822,16 @@ __global__ void __launch_bounds__(256, sizeof(R) == 4 ? 2 : 1) fused_bwd_kernel(
 
         V *tpsi = reinterpret_cast<V *>(buf_psi);
         V *tg = reinterpret_cast<V *>(buf_g);
-        for (int g = a.num_gates - 1; g >= 0; --g) {
+        if constexpr (sizeof(R) == 4) {
+            if (ba.ncl > 0) {
+                for (int c = 0; c < ba.ncl; ++c) {
+                    bwd_cluster_run(reinterpret_cast<float2 *>(buf_psi), reinterpret_cast<float2 *>(buf_g), ba, c,
+                                    reinterpret_cast<const float2 *>(sM), sAcc, a.T, NT);
+                    __syncthreads();
+                }
+            }
+        }
+        for (int g = (sizeof(R) == 4 && ba.ncl > 0) ? -1 : a.num_gates - 1; g >= 0; --g) {
             const FusedGate &gd = a.gates[g];
             const bool ng = (ba.needs_grad >> g) & 1ull;
             const C *M = sM + gd.smoff;
@@ -929,17 +1162,54 @@ extern "C" int ua_fused_backward_pass(int dtype, void *psi, void *grad, long lon
                                    tile_low_bits, num_high, host_high_pos, num_gates, host_gate_k,
                                    host_gate_bits, host_gate_offset, gate_mats, gate_row_stride, 1, 2, &mat_elems);
     if (rc) return rc;
-    ba.f.trank = 0;
-    setup_tensor_maps(ba.f, dtype == UA_C64 ? 0 : 1, total_amps);
     ba.acc = reinterpret_cast<double2 *>(grad_acc);
     ba.mat_elems = mat_elems;
     ba.needs_grad = 0;
     for (int g = 0; g < num_gates; ++g)
         if (host_gate_needs_grad[g]) ba.needs_grad |= 1ull << g;
+    // complex64: cut the reversed gate list into runs of consecutive gates on <= 4 tile bits
+    ba.ncl = 0;
+    { const char *e = getenv("UA_BWD_CLUSTER");
+      if (dtype == UA_C64 && ba.f.T >= 4 && !(e && atoi(e) == 0)) {
+        int g = num_gates - 1;
+        while (g >= 0) {
+            unsigned mask = 0;
+            const int first = g;
+            while (g >= 0) {
+                const FusedGate &gd = ba.f.gates[g];
+                unsigned gm = 0;
+                for (int i = 0; i < gd.k; ++i) gm |= 1u << gd.sb[i];
+                if (__builtin_popcount(mask | gm) > 4) break;
+                mask |= gm;
+                --g;
+            }
+            // pad to four bits from the top of the tile: the thread index then runs over the low bits
+            for (int b = ba.f.T - 1; b >= 0 && __builtin_popcount(mask) < 4; --b)
+                if (!((mask >> b) & 1u)) mask |= 1u << b;
+            const int c = ba.ncl++;
+            ba.cl_first[c] = (unsigned char)first;
+            ba.cl_count[c] = (unsigned char)(first - g);
+            int pos_of[32], nb = 0;
+            for (int b = 0; b < ba.f.T; ++b)
+                if ((mask >> b) & 1u) { ba.cl_bits[c][nb] = (unsigned char)b; pos_of[b] = nb; ++nb; }
+            for (int q = first; q > g; --q) {
+                const FusedGate &gd = ba.f.gates[q];
+                static const int pair_type[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+                ba.gtype[q] = (unsigned char)(gd.k == 1 ? 6 + pos_of[gd.sb[0]] : pair_type[pos_of[gd.sb[0]]][pos_of[gd.sb[1]]]);
+            }
+        }
+      } }
+    // the register-blocked form works on 128-byte-swizzled tiles; when the tile does not fit a
+    // swizzled tensor map (more than 5 dimensions with the first one fixed to bits 0..3) the pass
+    // runs in the per-gate form on plain tiles
+    ba.f.trank = 0;
+    if (ba.ncl > 0 && !setup_tensor_maps(ba.f, 0, total_amps, true)) { ba.ncl = 0; ba.f.trank = 0; }
+    if (ba.ncl == 0) setup_tensor_maps(ba.f, dtype == UA_C64 ? 0 : 1, total_amps);
     const size_t csize = (dtype == UA_C64) ? 8 : 16;
-    const size_t tile_bytes = ((size_t)1 << ba.f.T) * csize;
+    size_t tile_bytes = ((size_t)1 << ba.f.T) * csize;
+    if (tile_bytes < 1024) tile_bytes = 1024;
     const size_t mat_bytes = (((size_t)mat_elems * csize) + 127) & ~(size_t)127;
-    const size_t smem = 2 * tile_bytes + mat_bytes + (size_t)mat_elems * sizeof(double2);
+    const size_t smem = 2 * tile_bytes + mat_bytes + (size_t)mat_elems * sizeof(double2) + 1024;
     if (smem > 200 * 1024) { set_error("ua_fused_backward_pass: tile too large (%zu bytes of shared memory)", smem); return UA_ERR_UNSUPPORTED; }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
