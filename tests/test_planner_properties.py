@@ -167,3 +167,48 @@ def test_epoch_plan_reproduces_the_circuit_in_both_exchange_formulations(case, g
     epochs, end = sharded.plan_epochs([qs for qs, _ in gates], n, g, restore=restore, min_victim_bit=min_victim)
     got = _simulate_plan(epochs, end, gates, n, g, state, fused)
     assert _close(got, _run(gates, state))
+
+
+@settings(**SETTINGS)
+@given(gate_lists(max_qubits=7, max_k=2, max_gates=14), st.integers(1, 2), st.integers(2, 3), st.booleans())
+def test_joint_plan_of_repeated_steps_equals_chained_per_step_plans(case, g, steps, fused):
+    """bench.py plans the K timed steps of a sharded run as ONE gate list (the leftover gates of a
+    step share the next step's exchange).  That plan and K per-step plans chained through the qubit
+    layout must both reproduce K applications of the circuit, and the joint plan never needs more
+    exchanges than the chain."""
+    n, gates, state = case
+    g = min(g, n - 2)
+    qubits = [qs for qs, _ in gates]
+    want = np.array(state)
+    for _ in range(steps):
+        want = _run(gates, want)
+    epochs, end = sharded.plan_epochs(qubits * steps, n, g, restore=False)
+    got = _simulate_plan(epochs, end, gates * steps, n, g, state, fused)
+    assert _close(got, want)
+    joint_swaps = sum(1 for ep in epochs if ep.incoming)
+    # chained per-step plans: each starts in the layout the previous one ended in; simulated on the
+    # physical state by composing the plans' epoch lists
+    layout, chain_swaps = None, 0
+    phys = None
+    all_epochs = []
+    for _ in range(steps):
+        eps, layout = sharded.plan_epochs(qubits, n, g, layout=layout, restore=False)
+        chain_swaps += sum(1 for ep in eps if ep.incoming)
+        all_epochs.append(eps)
+    full = np.array(state)
+    n_local = n - g
+    for eps in all_epochs:
+        for ep in eps:
+            if ep.incoming and fused:
+                full = _scatter(full, n, n_local, ep)
+            else:
+                if ep.perm_src is not None:
+                    full = _permute_local_bits(full, n, n_local, ep.perm_src)
+                if ep.incoming:
+                    full = _exchange_bits(full, n, n_local, ep.rank_bits)
+            for gi, bits in zip(ep.gates, ep.local_bits):
+                full = orc.apply_operator(gates[gi][1], [n - 1 - p for p in bits], full)
+    t = full.reshape((2,) * n)
+    chained = np.transpose(t, [n - 1 - layout[q] for q in range(n)]).reshape(-1)
+    assert _close(chained, want)
+    assert joint_swaps <= chain_swaps
